@@ -1,0 +1,827 @@
+// fdtd_capi.cu -- implementation of the C ABI declared in include/fdtd_b200.h.
+//
+// Host-side control of the hot path.  Mirrors, call for call, what the reference's classes do:
+//   fdtd_create*        FDTD::FDTD / FDTD_PML::FDTD_PML    src/FDTD/FDTD.cpp:3-61, src/FDTD/FDTD_PML.cpp:205-341
+//   fdtd_update_fields  FDTD::update_fields                src/FDTD/FDTD.cpp:153-157, src/FDTD/FDTD_PML.cpp:343-365
+//   fdtd_zeroed_currents FDTD::zeroed_currents             src/FDTD/FDTD.cpp:132-136
+//   fdtd_upload/download/scatter/gather  = reads and writes through `Field& get_field(Component)`, FDTD.cpp:138-151
+// There is no CPU implementation behind any of these: without a usable CUDA device they fail.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "fused_kernel.cuh"
+#include "solver.h"
+#include "sweep_kernels.cuh"
+
+namespace fdtd_b200 {
+
+// include/Constants.h:6-11 of the reference -- these literals are part of the numerical spec
+static const double kC = 3e10;
+static const double kR = 1e-12;
+static const double kN = 4.0;
+static const double kPI = 3.14159265358;
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+fdtd_status_t fail(fdtd_status_t code, const std::string& msg) { g_err = msg; return code; }
+fdtd_status_t cuda_fail(cudaError_t e, const char* what) {
+    return fail(FDTD_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+}
+
+static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------------
+// PML tables (host, libm) -- src/FDTD/FDTD_PML.cpp:3-65, 98-111, 254-256, 293-338
+// ------------------------------------------------------------------------------------------------------
+static void pml_profile_host(int N, int p, double d, double dt, double* sigma, double* decay, double* coef2) {
+    const double cE = (kC * dt) / d;
+    double SGm = 0.0;
+    if (p > 0) SGm = -(kN + 1.0) / 2.0 * std::log(kR) / (static_cast<double>(p) * d);
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+        if (i < p) s = SGm * std::pow(static_cast<double>(p - i) / static_cast<double>(p), kN);
+        else if (i >= N - p) s = SGm * std::pow(static_cast<double>(i + 1 + p - N) / static_cast<double>(p), kN);
+        const double dec = std::exp(-s * dt * kC);
+        if (sigma) sigma[i] = s;
+        decay[i] = dec;
+        coef2[i] = (s != 0.0) ? (1.0 - dec) / (s * d) : cE;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// typed helpers
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static Fields<T> make_fields(const Solver* s) {
+    Fields<T> f;
+    for (int c = 0; c < 3; ++c) {
+        f.E[c] = static_cast<T*>(s->p[EX + c][s->cur]);
+        f.B[c] = static_cast<T*>(s->p[BX + c][s->cur]);
+        f.J[c] = static_cast<T*>(s->p[JX + c][0]);
+    }
+    for (int c = 0; c < NSPLIT; ++c) {
+        f.SE[c] = static_cast<T*>(s->split_p[c]);
+        f.SB[c] = static_cast<T*>(s->split_p[NSPLIT + c]);
+    }
+    return f;
+}
+
+static PmlDesc make_pml(const Solver* s) {
+    PmlDesc p;
+    for (int a = 0; a < 3; ++a) {
+        p.lo[a] = s->main_lo[a];
+        p.hi[a] = s->main_hi[a];
+        p.decay[a] = s->d_decay[a];
+        p.coef2[a] = s->d_coef2[a];
+    }
+    return p;
+}
+
+static int pick_kc(const Solver* s, int tiles_ij, int nplanes) {
+    // enough CTAs for several waves on 148 SMs, chunks long enough to amortise the k prologue
+    int kc = 32;
+    while (kc > 4 && (long long)tiles_ij * ((nplanes + kc - 1) / kc) < 148 * 8) kc /= 2;
+    if (kc > nplanes) kc = nplanes > 0 ? nplanes : 1;
+    (void)s;
+    return kc;
+}
+
+template <typename T>
+static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) {
+    constexpr int V = VecOf<T>::V;
+    SweepArgs<T> a;
+    a.g = s->g; a.c = s->c; a.p = make_pml(s); a.f = make_fields<T>(s); a.jbox = s->jbox;
+    a.k_lo = 0; a.k_hi = s->g.nk;
+    a.n_half = n_half; a.do_pml = do_pml;
+    a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
+    dim3 block(SWEEP_BX, SWEEP_BY);
+    const int gx = (s->g.Ni + SWEEP_BX * V - 1) / (SWEEP_BX * V);
+    const int gy = (s->g.Nj + SWEEP_BY - 1) / SWEEP_BY;
+    a.kc = pick_kc(s, gx * gy, s->g.nk);
+    const int gz = (s->g.nk + a.kc - 1) / a.kc;
+    dim3 grid(gx, gy, gz);
+    if (is_B) {
+        if (s->has_pml) sweep_B_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
+        else sweep_B_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
+    } else {
+        if (s->has_pml) sweep_E_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
+        else sweep_E_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
+    }
+    FDTD_CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    return FDTD_OK;
+}
+
+// Variant table of the fused pass (BY warps x RJ rows per warp); FDTD_B200_FUSED_VARIANT picks one.
+// (read on every launch so that tools/sweep.py can walk the table inside one process)
+static int fused_variant() {
+    const char* e = std::getenv("FDTD_B200_FUSED_VARIANT");
+    int v = e ? std::atoi(e) : 0;
+    if (v < 0 || v > 5) v = 0;
+    return v;
+}
+static int fused_kc_override() {
+    const char* e = std::getenv("FDTD_B200_FUSED_KC");
+    return e ? std::atoi(e) : 0;
+}
+
+template <typename T, int BY, int RJ, int MINB>
+static cudaError_t launch_fused_variant(Solver* s, FusedArgs<T>& a) {
+    constexpr int V = VecOf<T>::V;
+    constexpr int TIU = FUSED_OUT_LANES * V;
+    constexpr int TJU = BY * RJ - 2;
+    const int gx = (s->g.Ni + TIU - 1) / TIU;
+    const int gy = (s->g.Nj + TJU - 1) / TJU;
+    const int np = a.k_hi - a.k_lo;
+    int kc = fused_kc_override();
+    if (kc <= 0) {
+        kc = 64;
+        while (kc > 8 && (long long)gx * gy * ((np + kc - 1) / kc) < 148 * 6) kc /= 2;
+    }
+    if (kc > np) kc = np;
+    a.kc = kc;
+    const int gz = (np + kc - 1) / kc;
+    fused_BE_kernel<T, BY, RJ, MINB><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), 0, s->stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
+    FusedArgs<T> a;
+    a.g = s->g; a.c = s->c; a.jbox = s->jbox;
+    for (int c = 0; c < 3; ++c) {
+        a.Ein[c] = static_cast<const T*>(s->p[EX + c][s->cur]);
+        a.Bin[c] = static_cast<const T*>(s->p[BX + c][s->cur]);
+        a.Eout[c] = static_cast<T*>(s->p[EX + c][s->cur ^ 1]);
+        a.Bout[c] = static_cast<T*>(s->p[BX + c][s->cur ^ 1]);
+        a.J[c] = static_cast<const T*>(s->p[JX + c][0]);
+    }
+    a.k_lo = k_lo; a.k_hi = k_hi; a.n_half = n_half;
+    a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
+    cudaError_t e;
+    switch (fused_variant()) {
+        default:
+        case 0: e = launch_fused_variant<T, 8, 1, 2>(s, a); break;
+        case 1: e = launch_fused_variant<T, 12, 1, 1>(s, a); break;
+        case 2: e = launch_fused_variant<T, 8, 2, 1>(s, a); break;
+        case 3: e = launch_fused_variant<T, 4, 2, 2>(s, a); break;
+        case 4: e = launch_fused_variant<T, 10, 1, 2>(s, a); break;
+        case 5: e = launch_fused_variant<T, 8, 1, 3>(s, a); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "fused_BE_kernel launch");
+    s->launches++;
+    return FDTD_OK;
+}
+
+template <typename T>
+static fdtd_status_t launch_source(Solver* s, double amp, int zero) {
+    SourceArgs sa;
+    for (int a = 0; a < 3; ++a) { sa.lo[a] = s->src_lo[a]; sa.hi[a] = s->src_hi[a]; sa.w[a] = s->d_w[a]; }
+    sa.amp = amp; sa.zero = zero;
+    const long long total = (long long)(sa.hi[0] - sa.lo[0]) * (sa.hi[1] - sa.lo[1]) * (sa.hi[2] - sa.lo[2]);
+    if (total <= 0) return FDTD_OK;
+    const int threads = 128;
+    long long blocks = (total + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    source_kernel<T><<<(int)blocks, threads, 0, s->stream>>>(static_cast<T*>(s->p[JX][0]), static_cast<T*>(s->p[JY][0]),
+                                                            static_cast<T*>(s->p[JZ][0]), s->g, sa);
+    FDTD_CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    return FDTD_OK;
+}
+
+#define DISPATCH(s, fn, ...) ((s)->dtype == FDTD_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+// ------------------------------------------------------------------------------------------------------
+// halo exchange (z-slab ring).  Plane -1 / plane nk of every array are the ghost planes.
+// ------------------------------------------------------------------------------------------------------
+static char* plane_ptr(const Solver* s, int comp, int gen, int local_plane) {
+    return static_cast<char*>(s->p[comp][gen]) + (long long)local_plane * s->g.plane * (long long)s->esz;
+}
+
+// Top ghost of Ex,Ey <- upper neighbour's bottom plane (coarray/fdtd.F90:97-98).
+static fdtd_status_t exchange_E_top(Solver* s) {
+    if (s->cfg.nranks <= 1 || s->ghosts_e_valid) return FDTD_OK;
+    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
+    const size_t bytes = (size_t)s->g.plane * s->esz;
+    PlaneXfer x[2];
+    for (int c = 0; c < 2; ++c)
+        x[c] = PlaneXfer{plane_ptr(s, EX + c, s->cur, 0), down, plane_ptr(s, EX + c, s->cur, s->g.nk), up, bytes};
+    fdtd_status_t st = nccl_exchange(s, x, 2, s->stream);
+    if (st == FDTD_OK) s->ghosts_e_valid = true;
+    return st;
+}
+
+// Bottom ghost of Bx,By <- lower neighbour's top plane (coarray/fdtd.F90:90-91).
+static fdtd_status_t exchange_B_bottom(Solver* s) {
+    if (s->cfg.nranks <= 1 || s->ghosts_b_valid) return FDTD_OK;
+    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
+    const size_t bytes = (size_t)s->g.plane * s->esz;
+    PlaneXfer x[2];
+    for (int c = 0; c < 2; ++c)
+        x[c] = PlaneXfer{plane_ptr(s, BX + c, s->cur, s->g.nk - 1), up, plane_ptr(s, BX + c, s->cur, -1), down, bytes};
+    fdtd_status_t st = nccl_exchange(s, x, 2, s->stream);
+    if (st == FDTD_OK) s->ghosts_b_valid = true;
+    return st;
+}
+
+// Everything the fused pass needs: bottom ghost of Bx,By,Ex,Ey,Ez (to rebuild B'(-1)) and top ghost of Ex,Ey.
+static fdtd_status_t exchange_fused(Solver* s) {
+    if (s->cfg.nranks <= 1 || s->ghosts_fused_valid) return FDTD_OK;
+    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
+    const size_t bytes = (size_t)s->g.plane * s->esz;
+    PlaneXfer x[7];
+    const int up_comps[5] = {BX, BY, EX, EY, EZ};
+    int n = 0;
+    for (int c = 0; c < 5; ++c)
+        x[n++] = PlaneXfer{plane_ptr(s, up_comps[c], s->cur, s->g.nk - 1), up, plane_ptr(s, up_comps[c], s->cur, -1), down, bytes};
+    for (int c = 0; c < 2; ++c)
+        x[n++] = PlaneXfer{plane_ptr(s, EX + c, s->cur, 0), down, plane_ptr(s, EX + c, s->cur, s->g.nk), up, bytes};
+    fdtd_status_t st = nccl_exchange(s, x, n, s->stream);
+    if (st == FDTD_OK) { s->ghosts_fused_valid = true; s->ghosts_e_valid = true; s->ghosts_b_valid = true; }
+    return st;
+}
+
+static void invalidate_ghosts(Solver* s) {
+    s->ghosts_e_valid = s->ghosts_b_valid = s->ghosts_fused_valid = false;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the step state machine
+// ------------------------------------------------------------------------------------------------------
+
+// Apply the deferred trailing B half step (main cells only; the PML shell advances once per step).
+static fdtd_status_t flush_pending(Solver* s) {
+    if (!s->b_pending) return FDTD_OK;
+    fdtd_status_t st = exchange_E_top(s);
+    if (st != FDTD_OK) return st;
+    st = DISPATCH(s, launch_sweep, s, true, 1, 0);
+    if (st != FDTD_OK) return st;
+    s->b_pending = false;
+    s->ghosts_b_valid = false;
+    s->ghosts_fused_valid = false;
+    return FDTD_OK;
+}
+
+static void jbox_union(Solver* s, const int lo[3], const int hi[3]) {
+    if (lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) return;
+    if (s->jbox.empty()) {
+        for (int a = 0; a < 3; ++a) { s->jbox.lo[a] = lo[a]; s->jbox.hi[a] = hi[a]; }
+        return;
+    }
+    for (int a = 0; a < 3; ++a) {
+        if (lo[a] < s->jbox.lo[a]) s->jbox.lo[a] = lo[a];
+        if (hi[a] > s->jbox.hi[a]) s->jbox.hi[a] = hi[a];
+    }
+}
+static void jbox_clear(Solver* s) {
+    for (int a = 0; a < 3; ++a) { s->jbox.lo[a] = 0; s->jbox.hi[a] = 0; }
+}
+static void jbox_full(Solver* s) {
+    s->jbox.lo[0] = s->jbox.lo[1] = s->jbox.lo[2] = 0;
+    s->jbox.hi[0] = s->g.Ni; s->jbox.hi[1] = s->g.Nj; s->jbox.hi[2] = s->g.Nk;
+}
+
+static fdtd_status_t zero_currents_impl(Solver* s) {
+    if (s->jbox.empty()) return FDTD_OK;   // J is already +0.0 everywhere
+    const long long vol = (long long)(s->jbox.hi[0] - s->jbox.lo[0]) * (s->jbox.hi[1] - s->jbox.lo[1]) *
+                          (s->jbox.hi[2] - s->jbox.lo[2]);
+    if (vol <= (1 << 16)) {
+        // small box: the source kernel with zero=1 writes +0.0 on the box only (the tables are not read)
+        int lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) { lo[a] = s->src_lo[a]; hi[a] = s->src_hi[a]; }
+        for (int a = 0; a < 3; ++a) { s->src_lo[a] = s->jbox.lo[a]; s->src_hi[a] = s->jbox.hi[a]; }
+        fdtd_status_t st = DISPATCH(s, launch_source, s, 0.0, 1);
+        for (int a = 0; a < 3; ++a) { s->src_lo[a] = lo[a]; s->src_hi[a] = hi[a]; }
+        if (st != FDTD_OK) return st;
+    } else {
+        const size_t bytes = (size_t)s->g.plane * (size_t)(s->g.nk + 2) * s->esz;
+        for (int c = JX; c <= JZ; ++c) FDTD_CUDA_TRY(cudaMemsetAsync(s->base[c][0], 0, bytes, s->stream));
+    }
+    jbox_clear(s);
+    return FDTD_OK;
+}
+
+static fdtd_status_t advance_one(Solver* s) {
+    fdtd_status_t st;
+    // device-resident source: write J for this step (kokkos_sample.cpp:91-108), or retire it (sample.cpp:84)
+    if (s->src_active) {
+        if (s->src_t < (int)s->src_amp.size()) {
+            st = DISPATCH(s, launch_source, s, s->src_amp[s->src_t], 0);
+            if (st != FDTD_OK) return st;
+            jbox_union(s, s->src_lo, s->src_hi);
+            s->src_t++;
+        } else {
+            s->src_active = false;
+            st = zero_currents_impl(s);
+            if (st != FDTD_OK) return st;
+        }
+    }
+    const int n_half = s->b_pending ? 2 : 1;
+    if (s->fused) {
+        st = exchange_fused(s);
+        if (st != FDTD_OK) return st;
+        st = DISPATCH(s, launch_fused, s, n_half, 0, s->g.nk);
+        if (st != FDTD_OK) return st;
+        s->cur ^= 1;
+    } else {
+        st = exchange_E_top(s);
+        if (st != FDTD_OK) return st;
+        st = DISPATCH(s, launch_sweep, s, true, n_half, 1);
+        if (st != FDTD_OK) return st;
+        s->ghosts_b_valid = false;
+        st = exchange_B_bottom(s);
+        if (st != FDTD_OK) return st;
+        st = DISPATCH(s, launch_sweep, s, false, 0, 0);
+        if (st != FDTD_OK) return st;
+    }
+    invalidate_ghosts(s);
+    s->b_pending = true;
+    s->steps_done++;
+    return FDTD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// creation / destruction
+// ------------------------------------------------------------------------------------------------------
+static void destroy_impl(Solver* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    nccl_destroy(s);
+    for (int c = 0; c < NCOMP; ++c)
+        for (int gdx = 0; gdx < 2; ++gdx)
+            if (s->base[c][gdx]) cudaFree(s->base[c][gdx]);
+    for (int c = 0; c < 2 * NSPLIT; ++c)
+        if (s->split_base[c]) cudaFree(s->split_base[c]);
+    for (int a = 0; a < 3; ++a) {
+        if (s->d_decay[a]) cudaFree(s->d_decay[a]);
+        if (s->d_coef2[a]) cudaFree(s->d_coef2[a]);
+        if (s->d_w[a]) cudaFree(s->d_w[a]);
+    }
+    if (s->d_stage) cudaFree(s->d_stage);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    if (s->ev_t0) cudaEventDestroy(s->ev_t0);
+    if (s->ev_t1) cudaEventDestroy(s->ev_t1);
+    if (s->ev_a) cudaEventDestroy(s->ev_a);
+    if (s->ev_b) cudaEventDestroy(s->ev_b);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static fdtd_status_t alloc_array(Solver* s, void** base, void** p) {
+    const size_t bytes = (size_t)s->g.plane * (size_t)(s->g.nk + 2) * s->esz;
+    cudaError_t e = cudaMalloc(base, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FDTD_ERR_NOMEM, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    FDTD_CUDA_TRY(cudaMemsetAsync(*base, 0, bytes, s->stream));   // FDTD.cpp:21-32: all fields start at zero
+    *p = static_cast<char*>(*base) + (size_t)s->g.plane * s->esz;
+    s->device_bytes += (int64_t)bytes;
+    return FDTD_OK;
+}
+
+static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
+    const fdtd_params_t& P = cfg->grid;
+    // FDTD.cpp:5-7
+    if (P.Ni <= 0 || P.Nj <= 0 || P.Nk <= 0 || !(cfg->dt > 0)) return fail(FDTD_ERR_INVALID_PARAMETERS, "ERROR: invalid parameters");
+    if (cfg->dtype != FDTD_F64 && cfg->dtype != FDTD_F32) return fail(FDTD_ERR_BAD_ARGUMENT, "unknown dtype");
+    if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(FDTD_ERR_BAD_ARGUMENT, "bad rank / nranks");
+    if (cfg->nranks > P.Nk) return fail(FDTD_ERR_BAD_ARGUMENT, "more ranks than k planes");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(FDTD_ERR_CUDA, "no CUDA device available: libfdtd_b200 has no CPU fallback");
+    }
+    int dev = cfg->device;
+    if (dev < 0) FDTD_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(FDTD_ERR_BAD_ARGUMENT, "device ordinal out of range");
+    FDTD_CUDA_TRY(cudaSetDevice(dev));
+
+    Solver* s = new (std::nothrow) Solver();
+    if (!s) return fail(FDTD_ERR_NOMEM, "out of host memory");
+    s->cfg = *cfg;
+    s->device = dev;
+    s->dtype = cfg->dtype;
+    s->esz = (cfg->dtype == FDTD_F32) ? 4 : 8;
+
+    int k_begin, k_end;
+    fdtd_slab_range(P.Nk, cfg->rank, cfg->nranks, &k_begin, &k_end);
+    s->g.Ni = P.Ni; s->g.Nj = P.Nj; s->g.Nk = P.Nk;
+    s->g.nk = k_end - k_begin;
+    s->g.k0 = k_begin;
+    s->g.wrap_k = (cfg->nranks == 1) ? 1 : 0;
+    s->g.pitch = (long long)round_up((size_t)P.Ni, 128 / s->esz);
+    s->g.plane = s->g.pitch * P.Nj;
+
+    // FDTD.cpp:43-53
+    const double cdt = kC * cfg->dt;
+    s->c.cEx = cdt / P.dx; s->c.cEy = cdt / P.dy; s->c.cEz = cdt / P.dz;
+    s->c.cBx = cdt / (2.0 * P.dx); s->c.cBy = cdt / (2.0 * P.dy); s->c.cBz = cdt / (2.0 * P.dz);
+    s->c.cJ = -4.0 * kPI * cfg->dt;
+
+    const int N[3] = {P.Ni, P.Nj, P.Nk};
+    const double d[3] = {P.dx, P.dy, P.dz};
+    for (int a = 0; a < 3; ++a) { s->main_lo[a] = 0; s->main_hi[a] = N[a]; }
+    if (cfg->pml_mode != FDTD_PML_NONE) {
+        s->has_pml = true;
+        for (int a = 0; a < 3; ++a) {
+            s->pml[a] = (cfg->pml_mode == FDTD_PML_PERCENT) ? fdtd_pml_thickness(N[a], cfg->pml_percent) : cfg->pml_thickness[a];
+            if (s->pml[a] < 0 || 2 * s->pml[a] > N[a]) {
+                delete s;
+                return fail(FDTD_ERR_INVALID_PARAMETERS, "ERROR: invalid parameters (PML thicker than half the grid)");
+            }
+            s->main_lo[a] = s->pml[a];          // FDTD_PML.cpp:260-269
+            s->main_hi[a] = N[a] - s->pml[a];
+        }
+    }
+
+    fdtd_status_t st = FDTD_OK;
+    auto bail = [&](fdtd_status_t code) { std::string keep = g_err; destroy_impl(s); g_err = keep; return code; };
+
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
+    if (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
+    cudaEventCreate(&s->ev_t0); cudaEventCreate(&s->ev_t1);
+    cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming);
+
+    // The fused pass serves the periodic solver with vector-aligned rows; everything else runs the two sweeps.
+    const int V = (int)(16 / s->esz);
+    s->fused = !s->has_pml && !(cfg->flags & FDTD_FLAG_NO_FUSION) && (P.Ni % V == 0);
+
+    for (int c = 0; c < NCOMP && st == FDTD_OK; ++c) {
+        st = alloc_array(s, &s->base[c][0], &s->p[c][0]);
+        if (st == FDTD_OK && s->fused && c < JX) st = alloc_array(s, &s->base[c][1], &s->p[c][1]);
+    }
+    if (st != FDTD_OK) return bail(st);
+    if (s->has_pml) {
+        for (int c = 0; c < 2 * NSPLIT && st == FDTD_OK; ++c) st = alloc_array(s, &s->split_base[c], &s->split_p[c]);   // FDTD_PML.cpp:209-252
+        if (st != FDTD_OK) return bail(st);
+        for (int a = 0; a < 3; ++a) {
+            std::vector<double> dec(N[a]), c2(N[a]);
+            pml_profile_host(N[a], s->pml[a], d[a], cfg->dt, nullptr, dec.data(), c2.data());
+            if (cudaMalloc(&s->d_decay[a], sizeof(double) * N[a]) != cudaSuccess ||
+                cudaMalloc(&s->d_coef2[a], sizeof(double) * N[a]) != cudaSuccess)
+                return bail(cuda_fail(cudaGetLastError(), "cudaMalloc(pml tables)"));
+            cudaMemcpy(s->d_decay[a], dec.data(), sizeof(double) * N[a], cudaMemcpyHostToDevice);
+            cudaMemcpy(s->d_coef2[a], c2.data(), sizeof(double) * N[a], cudaMemcpyHostToDevice);
+        }
+    }
+    jbox_clear(s);
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "initial zero fill"));
+    *out = s;
+    return FDTD_OK;
+}
+
+static fdtd_status_t check_handle(fdtd_solver_t* h, Solver** s) {
+    if (!h) return fail(FDTD_ERR_BAD_ARGUMENT, "null solver handle");
+    *s = reinterpret_cast<Solver*>(h);
+    cudaError_t e = cudaSetDevice((*s)->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return FDTD_OK;
+}
+
+static fdtd_status_t check_component(int comp) {
+    if (comp < EX || comp > JZ) return fail(FDTD_ERR_INVALID_COMPONENT, "ERROR: Invalid field component");   // FDTD.cpp:149
+    return FDTD_OK;
+}
+
+static fdtd_status_t ensure_stage(Solver* s, size_t bytes) {
+    if (bytes <= s->stage_bytes) return FDTD_OK;
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->d_stage) cudaFree(s->d_stage);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    s->d_stage = nullptr; s->h_stage = nullptr; s->stage_bytes = 0;
+    size_t cap = round_up(bytes < 4096 ? 4096 : bytes * 2, 256);
+    FDTD_CUDA_TRY(cudaMalloc(&s->d_stage, cap));
+    FDTD_CUDA_TRY(cudaMallocHost(&s->h_stage, cap));
+    s->stage_bytes = cap;
+    return FDTD_OK;
+}
+
+template <typename T>
+static fdtd_status_t scatter_impl(Solver* s, int comp, const int64_t* idx, const void* vals, size_t n) {
+    const size_t ib = round_up(n * sizeof(long long), 256), vb = n * sizeof(T);
+    fdtd_status_t st = ensure_stage(s, ib + vb);
+    if (st != FDTD_OK) return st;
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));   // staging buffer may still be in flight
+    std::memcpy(s->h_stage, idx, n * sizeof(long long));
+    std::memcpy(static_cast<char*>(s->h_stage) + ib, vals, vb);
+    FDTD_CUDA_TRY(cudaMemcpyAsync(s->d_stage, s->h_stage, ib + vb, cudaMemcpyHostToDevice, s->stream));
+    const int threads = 128, blocks = (int)((n + threads - 1) / threads);
+    scatter_kernel<T><<<blocks, threads, 0, s->stream>>>(static_cast<T*>(s->cur_ptr(comp)), s->g,
+                                                        static_cast<const long long*>(s->d_stage),
+                                                        reinterpret_cast<const T*>(static_cast<char*>(s->d_stage) + ib), (int)n);
+    FDTD_CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    return FDTD_OK;
+}
+
+template <typename T>
+static fdtd_status_t gather_impl(Solver* s, int comp, const int64_t* idx, void* vals, size_t n) {
+    const size_t ib = round_up(n * sizeof(long long), 256), vb = n * sizeof(T);
+    fdtd_status_t st = ensure_stage(s, ib + vb);
+    if (st != FDTD_OK) return st;
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    std::memcpy(s->h_stage, idx, n * sizeof(long long));
+    std::memcpy(static_cast<char*>(s->h_stage) + ib, vals, vb);   // entries not owned by this rank stay untouched
+    FDTD_CUDA_TRY(cudaMemcpyAsync(s->d_stage, s->h_stage, ib + vb, cudaMemcpyHostToDevice, s->stream));
+    const int threads = 128, blocks = (int)((n + threads - 1) / threads);
+    gather_kernel<T><<<blocks, threads, 0, s->stream>>>(static_cast<const T*>(s->cur_ptr(comp)), s->g,
+                                                       static_cast<const long long*>(s->d_stage),
+                                                       reinterpret_cast<T*>(static_cast<char*>(s->d_stage) + ib), (int)n);
+    FDTD_CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    FDTD_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(s->h_stage) + ib, static_cast<char*>(s->d_stage) + ib, vb,
+                                  cudaMemcpyDeviceToHost, s->stream));
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    std::memcpy(vals, static_cast<char*>(s->h_stage) + ib, vb);
+    return FDTD_OK;
+}
+
+}  // namespace fdtd_b200
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+using namespace fdtd_b200;
+
+extern "C" {
+
+const char* fdtd_last_error(void) { return g_err.c_str(); }
+int fdtd_version(void) { return FDTD_B200_VERSION; }
+
+int fdtd_pml_thickness(int N, double pml_percent) {
+    return static_cast<int>(static_cast<double>(N) * pml_percent);   // FDTD_PML.cpp:254-256
+}
+
+fdtd_status_t fdtd_pml_profile(int N, int thickness, double d, double dt, double* sigma, double* decay, double* coef2) {
+    if (N <= 0 || thickness < 0 || 2 * thickness > N || !decay || !coef2) return fail(FDTD_ERR_BAD_ARGUMENT, "bad PML profile request");
+    pml_profile_host(N, thickness, d, dt, sigma, decay, coef2);
+    return FDTD_OK;
+}
+
+void fdtd_slab_range(int Nk, int rank, int nranks, int* k_begin, int* k_end) {
+    const int base = Nk / nranks, rem = Nk % nranks;
+    const int b = rank * base + (rank < rem ? rank : rem);
+    if (k_begin) *k_begin = b;
+    if (k_end) *k_end = b + base + (rank < rem ? 1 : 0);
+}
+
+void fdtd_config_init(fdtd_config_t* cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(*cfg);
+    cfg->dtype = FDTD_F64;
+    cfg->pml_mode = FDTD_PML_NONE;
+    cfg->device = -1;
+    cfg->rank = 0;
+    cfg->nranks = 1;
+}
+
+fdtd_status_t fdtd_create_ex(const fdtd_config_t* cfg, fdtd_solver_t** out) {
+    if (!cfg || !out) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    if (cfg->struct_size != sizeof(fdtd_config_t)) return fail(FDTD_ERR_BAD_ARGUMENT, "fdtd_config_t size mismatch (use fdtd_config_init)");
+    Solver* s = nullptr;
+    fdtd_status_t st = create_impl(cfg, &s);
+    if (st != FDTD_OK) return st;
+    *out = reinterpret_cast<fdtd_solver_t*>(s);
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_create(const fdtd_params_t* params, double dt, fdtd_solver_t** out) {
+    if (!params) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    fdtd_config_t cfg;
+    fdtd_config_init(&cfg);
+    cfg.grid = *params;
+    cfg.dt = dt;
+    return fdtd_create_ex(&cfg, out);
+}
+
+fdtd_status_t fdtd_create_pml(const fdtd_params_t* params, double dt, double pml_percent, fdtd_solver_t** out) {
+    if (!params) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    fdtd_config_t cfg;
+    fdtd_config_init(&cfg);
+    cfg.grid = *params;
+    cfg.dt = dt;
+    cfg.pml_mode = FDTD_PML_PERCENT;
+    cfg.pml_percent = pml_percent;
+    return fdtd_create_ex(&cfg, out);
+}
+
+fdtd_status_t fdtd_destroy(fdtd_solver_t* h) {
+    if (!h) return FDTD_OK;
+    destroy_impl(reinterpret_cast<Solver*>(h));
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_step(fdtd_solver_t* h, int nsteps) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if (nsteps < 0) return fail(FDTD_ERR_BAD_ARGUMENT, "negative step count");
+    for (int t = 0; t < nsteps; ++t) {
+        st = advance_one(s);
+        if (st != FDTD_OK) return st;
+    }
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_update_fields(fdtd_solver_t* h) { return fdtd_step(h, 1); }
+
+fdtd_status_t fdtd_zeroed_currents(fdtd_solver_t* h) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    s->src_active = false;
+    return zero_currents_impl(s);
+}
+
+fdtd_status_t fdtd_upload(fdtd_solver_t* h, int comp, const void* host, size_t count) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if ((st = check_component(comp)) != FDTD_OK) return st;
+    const size_t expect = (size_t)s->g.Ni * s->g.Nj * s->g.nk;
+    if (!host || count != expect) return fail(FDTD_ERR_BAD_ARGUMENT, "upload: count must equal Ni*Nj*(k_end-k_begin)");
+    if (comp < JX) {
+        if ((st = flush_pending(s)) != FDTD_OK) return st;
+        invalidate_ghosts(s);
+    } else {
+        jbox_full(s);
+    }
+    FDTD_CUDA_TRY(cudaMemcpy2DAsync(s->cur_ptr(comp), (size_t)s->g.pitch * s->esz, host, (size_t)s->g.Ni * s->esz,
+                                    (size_t)s->g.Ni * s->esz, (size_t)s->g.Nj * s->g.nk, cudaMemcpyHostToDevice, s->stream));
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_download(fdtd_solver_t* h, int comp, void* host, size_t count) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if ((st = check_component(comp)) != FDTD_OK) return st;
+    const size_t expect = (size_t)s->g.Ni * s->g.Nj * s->g.nk;
+    if (!host || count != expect) return fail(FDTD_ERR_BAD_ARGUMENT, "download: count must equal Ni*Nj*(k_end-k_begin)");
+    if (comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
+    FDTD_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)s->g.Ni * s->esz, s->cur_ptr(comp), (size_t)s->g.pitch * s->esz,
+                                    (size_t)s->g.Ni * s->esz, (size_t)s->g.Nj * s->g.nk, cudaMemcpyDeviceToHost, s->stream));
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_scatter(fdtd_solver_t* h, int comp, const int64_t* idx, const void* values, size_t n) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if ((st = check_component(comp)) != FDTD_OK) return st;
+    if (n == 0) return FDTD_OK;
+    if (!idx || !values) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    const long long total = (long long)s->g.Ni * s->g.Nj * s->g.Nk, ij = (long long)s->g.Ni * s->g.Nj;
+    int lo[3] = {s->g.Ni, s->g.Nj, s->g.Nk}, hi[3] = {0, 0, 0};
+    for (size_t t = 0; t < n; ++t) {
+        if (idx[t] < 0 || idx[t] >= total) return fail(FDTD_ERR_BAD_ARGUMENT, "scatter: index out of range");
+        const int k = (int)(idx[t] / ij), j = (int)((idx[t] % ij) / s->g.Ni), i = (int)(idx[t] % s->g.Ni);
+        const int c3[3] = {i, j, k};
+        for (int a = 0; a < 3; ++a) { if (c3[a] < lo[a]) lo[a] = c3[a]; if (c3[a] + 1 > hi[a]) hi[a] = c3[a] + 1; }
+    }
+    if (comp < JX) {
+        if ((st = flush_pending(s)) != FDTD_OK) return st;
+        invalidate_ghosts(s);
+    } else {
+        jbox_union(s, lo, hi);
+    }
+    return (s->dtype == FDTD_F32) ? scatter_impl<float>(s, comp, idx, values, n) : scatter_impl<double>(s, comp, idx, values, n);
+}
+
+fdtd_status_t fdtd_gather(fdtd_solver_t* h, int comp, const int64_t* idx, void* values, size_t n) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if ((st = check_component(comp)) != FDTD_OK) return st;
+    if (n == 0) return FDTD_OK;
+    if (!idx || !values) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    const long long total = (long long)s->g.Ni * s->g.Nj * s->g.Nk;
+    for (size_t t = 0; t < n; ++t)
+        if (idx[t] < 0 || idx[t] >= total) return fail(FDTD_ERR_BAD_ARGUMENT, "gather: index out of range");
+    if (comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
+    return (s->dtype == FDTD_F32) ? gather_impl<float>(s, comp, idx, values, n) : gather_impl<double>(s, comp, idx, values, n);
+}
+
+fdtd_status_t fdtd_set_source(fdtd_solver_t* h, const int lo[3], const int hi[3], const double* wx, const double* wy,
+                              const double* wz, const double* amp, int n_amp) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if (!lo || !hi || !wx || !wy || !wz || !amp || n_amp < 0) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    const int N[3] = {s->g.Ni, s->g.Nj, s->g.Nk};
+    for (int a = 0; a < 3; ++a)
+        if (lo[a] < 0 || hi[a] > N[a] || lo[a] > hi[a]) return fail(FDTD_ERR_BAD_ARGUMENT, "source box outside the grid");
+    const double* w[3] = {wx, wy, wz};
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (int a = 0; a < 3; ++a) {
+        if (s->d_w[a]) { cudaFree(s->d_w[a]); s->d_w[a] = nullptr; }
+        const int n = hi[a] - lo[a];
+        if (n > 0) {
+            FDTD_CUDA_TRY(cudaMalloc(&s->d_w[a], sizeof(double) * n));
+            FDTD_CUDA_TRY(cudaMemcpy(s->d_w[a], w[a], sizeof(double) * n, cudaMemcpyHostToDevice));
+        }
+        s->src_lo[a] = lo[a]; s->src_hi[a] = hi[a];
+    }
+    s->src_amp.assign(amp, amp + n_amp);
+    s->src_t = 0;
+    s->src_active = true;
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_clear_source(fdtd_solver_t* h) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    s->src_active = false;
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_sync(fdtd_solver_t* h) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if ((st = flush_pending(s)) != FDTD_OK) return st;
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_device_ptr(fdtd_solver_t* h, int comp, void** dptr) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if ((st = check_component(comp)) != FDTD_OK) return st;
+    if (!dptr) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    if ((st = flush_pending(s)) != FDTD_OK) return st;
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (comp < JX) invalidate_ghosts(s); else jbox_full(s);   // the caller may write through the pointer
+    *dptr = s->cur_ptr(comp);
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_get_info(fdtd_solver_t* h, fdtd_info_t* info) {
+    if (!h || !info) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    Solver* s = reinterpret_cast<Solver*>(h);
+    std::memset(info, 0, sizeof(*info));
+    info->Ni = s->g.Ni; info->Nj = s->g.Nj; info->Nk = s->g.Nk;
+    info->k_begin = s->g.k0; info->k_end = s->g.k0 + s->g.nk;
+    info->dtype = s->dtype; info->has_pml = s->has_pml ? 1 : 0;
+    for (int a = 0; a < 3; ++a) info->pml_thickness[a] = s->pml[a];
+    info->pitch = s->g.pitch; info->plane = s->g.plane;
+    info->device_bytes = s->device_bytes;
+    info->launches = s->launches;
+    info->steps_done = s->steps_done;
+    info->fused = s->fused ? 1 : 0;
+    info->rank = s->cfg.rank; info->nranks = s->cfg.nranks; info->device = s->device;
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_timer_start(fdtd_solver_t* h) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    FDTD_CUDA_TRY(cudaEventRecord(s->ev_t0, s->stream));
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_timer_stop(fdtd_solver_t* h, double* elapsed_ms) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    FDTD_CUDA_TRY(cudaEventRecord(s->ev_t1, s->stream));
+    FDTD_CUDA_TRY(cudaEventSynchronize(s->ev_t1));
+    float ms = 0.f;
+    FDTD_CUDA_TRY(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
+    if (elapsed_ms) *elapsed_ms = (double)ms;
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_get_stream(fdtd_solver_t* h, void** stream) {
+    if (!h || !stream) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    *stream = reinterpret_cast<Solver*>(h)->stream;
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_nccl_unique_id(void* id_out, size_t capacity) { return nccl_unique_id(id_out, capacity); }
+
+fdtd_status_t fdtd_comm_init(fdtd_solver_t* h, const void* id, size_t id_bytes) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    return nccl_init(s, id, id_bytes);
+}
+
+}  // extern "C"

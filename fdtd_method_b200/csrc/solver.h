@@ -1,0 +1,94 @@
+// solver.h -- host-side state of one fdtd_solver_t (one GPU, one z-slab).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fdtd_b200.h"
+#include "fdtd_common.cuh"
+
+namespace fdtd_b200 {
+
+struct NcclApi;   // dlopen'ed libnccl entry points (nccl_ring.cu)
+
+struct Solver {
+    fdtd_config_t cfg{};
+    int device = 0;
+    int dtype = FDTD_F64;
+    size_t esz = 8;
+    Geom g{};
+    Coefs c{};
+    bool has_pml = false;
+    int pml[3] = {0, 0, 0};
+    int main_lo[3] = {0, 0, 0}, main_hi[3] = {0, 0, 0};
+    double* d_decay[3] = {nullptr, nullptr, nullptr};
+    double* d_coef2[3] = {nullptr, nullptr, nullptr};
+
+    // Device arrays.  base[] are the cudaMalloc pointers ((nk+2) planes); p[] = base + one plane.
+    // E and B have two generations (ping-pong) when the fused pass is enabled; cur selects the live one.
+    void* base[NCOMP][2] = {};
+    void* p[NCOMP][2] = {};
+    void* split_base[2 * NSPLIT] = {};
+    void* split_p[2 * NSPLIT] = {};
+    int cur = 0;
+    bool fused = false;
+    int64_t device_bytes = 0;
+
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr;
+
+    // Deferred trailing B half step: after update_fields() the device holds E(n+1) and B(n+1/2);
+    // the missing half step is merged into the next step's leading half step (B = (B+h)+h) or applied
+    // by flush() before anything reads or overwrites E/B.  Bit-identical either way.
+    bool b_pending = false;
+    bool ghosts_e_valid = false;   // top ghost planes of Ex, Ey hold the upper neighbour's current plane
+    bool ghosts_b_valid = false;   // bottom ghost planes of Bx, By hold the lower neighbour's current plane
+    bool ghosts_fused_valid = false;
+
+    JBox jbox{};                   // where J may be non-zero
+    // device-resident source (fdtd_set_source)
+    bool src_active = false;
+    int src_lo[3] = {}, src_hi[3] = {};
+    double* d_w[3] = {nullptr, nullptr, nullptr};
+    std::vector<double> src_amp;
+    int src_t = 0;
+
+    // staging for scatter / gather
+    void* h_stage = nullptr;       // pinned
+    void* d_stage = nullptr;
+    size_t stage_bytes = 0;
+
+    // NCCL ring
+    NcclApi* nccl = nullptr;
+    void* comm = nullptr;
+
+    int64_t launches = 0;
+    int64_t steps_done = 0;
+
+    void* cur_ptr(int comp) const { return p[comp][(comp < JX) ? cur : 0]; }
+};
+
+// thread-local error message (fdtd_last_error)
+void set_error(const std::string& msg);
+fdtd_status_t fail(fdtd_status_t code, const std::string& msg);
+fdtd_status_t cuda_fail(cudaError_t e, const char* what);
+
+#define FDTD_CUDA_TRY(expr)                                                     \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess) return ::fdtd_b200::cuda_fail(_e, #expr);        \
+    } while (0)
+
+// nccl_ring.cu
+fdtd_status_t nccl_unique_id(void* out, size_t cap);
+fdtd_status_t nccl_init(Solver* s, const void* id, size_t bytes);
+void nccl_destroy(Solver* s);
+// Grouped ring exchange of whole planes.  Each entry: send `bytes` from `send` to `peer_send`,
+// receive `bytes` into `recv` from `peer_recv`.
+struct PlaneXfer { const void* send; int peer_send; void* recv; int peer_recv; size_t bytes; };
+fdtd_status_t nccl_exchange(Solver* s, const PlaneXfer* x, int n, cudaStream_t stream);
+
+}  // namespace fdtd_b200

@@ -1,0 +1,399 @@
+// sweep_kernels.cuh -- the general two-sweep path: one B sweep and one E sweep per Yee step.
+//
+// These kernels serve every configuration (periodic / PML, fp64 / fp32, single GPU / z-slab rank);
+// the fused E+B pass in fused_kernel.cuh is the fast path for the periodic solver.
+//
+//   sweep_B_kernel  replaces FDTD::update_B           (reference src/FDTD/FDTD.cpp:99-130,
+//                                                       include/FDTD_kokkos/kokkos_functors.h:128-151)
+//                   and     FDTD_PML::update_B_PML x6 (src/FDTD/FDTD_PML.cpp:136-203, call sites :346-352)
+//   sweep_E_kernel  replaces FDTD::update_E           (src/FDTD/FDTD.cpp:63-97, kokkos_functors.h:64-90)
+//                   and     FDTD_PML::update_E_PML x6 (src/FDTD/FDTD_PML.cpp:67-134, call sites :356-362)
+//
+// Differences from the reference's structure, none of which change a single bit of the result:
+//   * the reference's trailing B half step of step s and leading B half step of step s+1 see the same
+//     E, so they are applied together as B = (B + h) + h (n_half = 2) -- two sweeps per step, not three;
+//   * the six PML shell boxes and the main box are one launch with a per-cell region predicate
+//     (each phase only reads the other field family);
+//   * sigma is a function of one coordinate, so exp()/division live in host-computed 1-D tables;
+//   * the current term is skipped outside the bounding box where J may be non-zero
+//     (cJ * (+0.0) = -0.0 and x + (-0.0) == x, so the skip is exact).
+//
+// Mapping: one thread owns V = 16 B / sizeof(T) consecutive cells in i (one 128-bit load/store per
+// array), a warp covers 32*V contiguous cells of one row, a CTA 8 rows, and each thread streams a
+// chunk of k planes keeping the k-neighbour in registers.  j/k neighbours are whole-row offsets;
+// the i neighbour of the last lane is one extra (L1-resident) scalar load.
+#pragma once
+
+#include "fdtd_common.cuh"
+
+namespace fdtd_b200 {
+
+template <typename T>
+struct SweepArgs {
+    Geom g;
+    Coefs c;
+    PmlDesc p;
+    Fields<T> f;
+    JBox jbox;
+    int k_lo, k_hi;     // local plane range [k_lo, k_hi) this launch covers
+    int kc;             // planes per thread (k chunk)
+    int n_half;         // B sweep: 1 or 2 half steps on main cells (0: leave main cells untouched)
+    int do_pml;         // B sweep: also advance the PML shell (full step)
+    int j_quirk;        // E sweep: FDTD_openmp semantics, Jx feeds all three components
+};
+
+constexpr int SWEEP_BX = 32;  // lanes along i
+constexpr int SWEEP_BY = 8;   // rows along j
+
+template <typename T, bool PML>
+__global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const SweepArgs<T> a) {
+    constexpr int V = VecOf<T>::V;
+    const int Ni = a.g.Ni, Nj = a.g.Nj;
+    const int i0 = (blockIdx.x * SWEEP_BX + threadIdx.x) * V;
+    const int j = blockIdx.y * SWEEP_BY + threadIdx.y;
+    if (i0 >= Ni || j >= Nj) return;
+    const int kb = a.k_lo + blockIdx.z * a.kc;
+    const int ke = min(kb + a.kc, a.k_hi);
+    if (kb >= ke) return;
+
+    const int nvalid = min(V, Ni - i0);
+    const int jn = (j + 1 == Nj) ? 0 : j + 1;
+    const int cn = (i0 + V < Ni) ? i0 + V : 0;   // column right of this thread's last cell (wrapped)
+    const long long row = (long long)j * a.g.pitch;
+    const long long rown = (long long)jn * a.g.pitch;
+
+    const T* __restrict__ Ex = a.f.E[0];
+    const T* __restrict__ Ey = a.f.E[1];
+    const T* __restrict__ Ez = a.f.E[2];
+    T* __restrict__ Bx = a.f.B[0];
+    T* __restrict__ By = a.f.B[1];
+    T* __restrict__ Bz = a.f.B[2];
+    const double cx = a.c.cBx, cy = a.c.cBy, cz = a.c.cBz;
+
+    bool col_main[V];
+    double dcx[V], c2x[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        col_main[e] = true;
+        dcx[e] = 1.0; c2x[e] = 0.0;
+        if (PML) {
+            const int i = min(i0 + e, Ni - 1);
+            col_main[e] = (i >= a.p.lo[0] && i < a.p.hi[0]);
+            dcx[e] = a.p.decay[0][i];
+            c2x[e] = a.p.coef2[0][i];
+        }
+    }
+    bool jrow_main = true;
+    double dcy = 1.0, c2y = 0.0;
+    if (PML) {
+        jrow_main = (j >= a.p.lo[1] && j < a.p.hi[1]);
+        dcy = a.p.decay[1][j];
+        c2y = a.p.coef2[1][j];
+    }
+
+    double ex[V], ey[V];
+    {
+        const long long o = (long long)kb * a.g.plane + row + i0;
+        ldv(Ex + o, ex);
+        ldv(Ey + o, ey);
+    }
+    for (int k = kb; k < ke; ++k) {
+        int kn = k + 1;
+        if (kn == a.g.nk && a.g.wrap_k) kn = 0;
+        const long long pk = (long long)k * a.g.plane;
+        const long long pkn = (long long)kn * a.g.plane;
+        const long long o = pk + row + i0;
+
+        double exn[V], eyn[V], ez[V], ezj[V], exj[V], bx[V], by[V], bz[V];
+        ldv(Ex + pkn + row + i0, exn);
+        ldv(Ey + pkn + row + i0, eyn);
+        ldv(Ez + o, ez);
+        ldv(Ez + pk + rown + i0, ezj);
+        ldv(Ex + pk + rown + i0, exj);
+        const double ez_r = lds1(Ez + pk + row + cn);
+        const double ey_r = lds1(Ey + pk + row + cn);
+        ldv(Bx + o, bx);
+        ldv(By + o, by);
+        ldv(Bz + o, bz);
+
+        bool row_main = jrow_main;
+        double dcz = 1.0, c2z = 0.0;
+        if (PML) {
+            const int kg = a.g.k0 + k;
+            row_main = row_main && (kg >= a.p.lo[2] && kg < a.p.hi[2]);
+            dcz = a.p.decay[2][kg];
+            c2z = a.p.coef2[2][kg];
+        }
+        bool any_pml = false;
+        if (PML) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) any_pml = any_pml || (e < nvalid && !(row_main && col_main[e]));
+            any_pml = any_pml && a.do_pml;
+        }
+        double sxy[V], sxz[V], syx[V], syz[V], szx[V], szy[V];
+        if (PML && any_pml) {
+            ldv(a.f.SB[S_XY] + o, sxy); ldv(a.f.SB[S_XZ] + o, sxz);
+            ldv(a.f.SB[S_YX] + o, syx); ldv(a.f.SB[S_YZ] + o, syz);
+            ldv(a.f.SB[S_ZX] + o, szx); ldv(a.f.SB[S_ZY] + o, szy);
+        }
+
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            // right (i+1) neighbours: own next element, or the wrapped/next-thread scalar
+            const bool use_scalar = (e == V - 1) || (i0 + e + 1 == Ni);
+            const double ezr = use_scalar ? ez_r : ez[(e + 1) % V];
+            const double eyr = use_scalar ? ey_r : ey[(e + 1) % V];
+            const double dEy_k = dsub(eyn[e], ey[e]);
+            const double dEz_j = dsub(ezj[e], ez[e]);
+            const double dEz_i = dsub(ezr, ez[e]);
+            const double dEx_k = dsub(exn[e], ex[e]);
+            const double dEx_j = dsub(exj[e], ex[e]);
+            const double dEy_i = dsub(eyr, ey[e]);
+            if (!PML || (row_main && col_main[e])) {
+                // FDTD.cpp:121-126
+                const double hx = dsub(dmul(cz, dEy_k), dmul(cy, dEz_j));
+                const double hy = dsub(dmul(cx, dEz_i), dmul(cz, dEx_k));
+                const double hz = dsub(dmul(cy, dEx_j), dmul(cx, dEy_i));
+                if (a.n_half >= 1) {
+                    bx[e] = round_store<T>(dadd(bx[e], hx));
+                    by[e] = round_store<T>(dadd(by[e], hy));
+                    bz[e] = round_store<T>(dadd(bz[e], hz));
+                }
+                if (a.n_half >= 2) {
+                    bx[e] = round_store<T>(dadd(bx[e], hx));
+                    by[e] = round_store<T>(dadd(by[e], hy));
+                    bz[e] = round_store<T>(dadd(bz[e], hz));
+                }
+            } else if (PML && a.do_pml) {
+                // FDTD_PML.cpp:182-199
+                syx[e] = round_store<T>(dadd(dmul(syx[e], dcx[e]), dmul(c2x[e], dEz_i)));
+                szx[e] = round_store<T>(dsub(dmul(szx[e], dcx[e]), dmul(c2x[e], dEy_i)));
+                sxy[e] = round_store<T>(dsub(dmul(sxy[e], dcy), dmul(c2y, dEz_j)));
+                szy[e] = round_store<T>(dadd(dmul(szy[e], dcy), dmul(c2y, dEx_j)));
+                sxz[e] = round_store<T>(dadd(dmul(sxz[e], dcz), dmul(c2z, dEy_k)));
+                syz[e] = round_store<T>(dsub(dmul(syz[e], dcz), dmul(c2z, dEx_k)));
+                bx[e] = round_store<T>(dadd(sxy[e], sxz[e]));
+                by[e] = round_store<T>(dadd(syz[e], syx[e]));
+                bz[e] = round_store<T>(dadd(szx[e], szy[e]));
+            }
+        }
+        stv(Bx + o, bx, nvalid);
+        stv(By + o, by, nvalid);
+        stv(Bz + o, bz, nvalid);
+        if (PML && any_pml) {
+            stv(a.f.SB[S_XY] + o, sxy, nvalid); stv(a.f.SB[S_XZ] + o, sxz, nvalid);
+            stv(a.f.SB[S_YX] + o, syx, nvalid); stv(a.f.SB[S_YZ] + o, syz, nvalid);
+            stv(a.f.SB[S_ZX] + o, szx, nvalid); stv(a.f.SB[S_ZY] + o, szy, nvalid);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) { ex[e] = exn[e]; ey[e] = eyn[e]; }
+    }
+}
+
+template <typename T, bool PML>
+__global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const SweepArgs<T> a) {
+    constexpr int V = VecOf<T>::V;
+    const int Ni = a.g.Ni, Nj = a.g.Nj;
+    const int i0 = (blockIdx.x * SWEEP_BX + threadIdx.x) * V;
+    const int j = blockIdx.y * SWEEP_BY + threadIdx.y;
+    if (i0 >= Ni || j >= Nj) return;
+    const int kb = a.k_lo + blockIdx.z * a.kc;
+    const int ke = min(kb + a.kc, a.k_hi);
+    if (kb >= ke) return;
+
+    const int nvalid = min(V, Ni - i0);
+    const int jp = (j == 0) ? Nj - 1 : j - 1;
+    const int cp = (i0 == 0) ? Ni - 1 : i0 - 1;   // column left of this thread's first cell (wrapped)
+    const long long row = (long long)j * a.g.pitch;
+    const long long rowp = (long long)jp * a.g.pitch;
+
+    T* __restrict__ Ex = a.f.E[0];
+    T* __restrict__ Ey = a.f.E[1];
+    T* __restrict__ Ez = a.f.E[2];
+    const T* __restrict__ Bx = a.f.B[0];
+    const T* __restrict__ By = a.f.B[1];
+    const T* __restrict__ Bz = a.f.B[2];
+    const T* __restrict__ Jx = a.f.J[0];
+    const T* __restrict__ Jy = a.j_quirk ? a.f.J[0] : a.f.J[1];
+    const T* __restrict__ Jz = a.j_quirk ? a.f.J[0] : a.f.J[2];
+    const double cx = a.c.cEx, cy = a.c.cEy, cz = a.c.cEz, cj = a.c.cJ;
+
+    bool col_main[V];
+    double dcx[V], c2x[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        col_main[e] = true;
+        dcx[e] = 1.0; c2x[e] = 0.0;
+        if (PML) {
+            const int i = min(i0 + e, Ni - 1);
+            col_main[e] = (i >= a.p.lo[0] && i < a.p.hi[0]);
+            dcx[e] = a.p.decay[0][i];
+            c2x[e] = a.p.coef2[0][i];
+        }
+    }
+    bool jrow_main = true;
+    double dcy = 1.0, c2y = 0.0;
+    if (PML) {
+        jrow_main = (j >= a.p.lo[1] && j < a.p.hi[1]);
+        dcy = a.p.decay[1][j];
+        c2y = a.p.coef2[1][j];
+    }
+    // Does this thread's (i, j) footprint touch the box where J may be non-zero?
+    const bool j_ij = !a.jbox.empty() && (i0 < a.jbox.hi[0] && i0 + V > a.jbox.lo[0]) &&
+                      (j >= a.jbox.lo[1] && j < a.jbox.hi[1]);
+
+    double bxm[V], bym[V];   // B at plane k-1
+    {
+        int km = kb - 1;
+        if (km < 0 && a.g.wrap_k) km = a.g.nk - 1;
+        const long long o = (long long)km * a.g.plane + row + i0;
+        ldv(Bx + o, bxm);
+        ldv(By + o, bym);
+    }
+    for (int k = kb; k < ke; ++k) {
+        const long long pk = (long long)k * a.g.plane;
+        const long long o = pk + row + i0;
+        const int kg = a.g.k0 + k;
+
+        double bx[V], by[V], bz[V], bzj[V], bxj[V], e_x[V], e_y[V], e_z[V];
+        ldv(Bx + o, bx);
+        ldv(By + o, by);
+        ldv(Bz + o, bz);
+        ldv(Bz + pk + rowp + i0, bzj);
+        ldv(Bx + pk + rowp + i0, bxj);
+        const double bz_l = lds1(Bz + pk + row + cp);
+        const double by_l = lds1(By + pk + row + cp);
+        ldv(Ex + o, e_x);
+        ldv(Ey + o, e_y);
+        ldv(Ez + o, e_z);
+
+        const bool use_j = j_ij && (kg >= a.jbox.lo[2] && kg < a.jbox.hi[2]);
+        double jx[V], jy[V], jz[V];
+        if (use_j) {
+            ldv(Jx + o, jx);
+            ldv(Jy + o, jy);
+            ldv(Jz + o, jz);
+        }
+
+        bool row_main = jrow_main;
+        double dcz = 1.0, c2z = 0.0;
+        if (PML) {
+            row_main = row_main && (kg >= a.p.lo[2] && kg < a.p.hi[2]);
+            dcz = a.p.decay[2][kg];
+            c2z = a.p.coef2[2][kg];
+        }
+        bool any_pml = false;
+        if (PML) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) any_pml = any_pml || (e < nvalid && !(row_main && col_main[e]));
+        }
+        double sxy[V], sxz[V], syx[V], syz[V], szx[V], szy[V];
+        if (PML && any_pml) {
+            ldv(a.f.SE[S_XY] + o, sxy); ldv(a.f.SE[S_XZ] + o, sxz);
+            ldv(a.f.SE[S_YX] + o, syx); ldv(a.f.SE[S_YZ] + o, syz);
+            ldv(a.f.SE[S_ZX] + o, szx); ldv(a.f.SE[S_ZY] + o, szy);
+        }
+
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const double bzl = (e == 0) ? bz_l : bz[(e + V - 1) % V];
+            const double byl = (e == 0) ? by_l : by[(e + V - 1) % V];
+            const double dBz_j = dsub(bz[e], bzj[e]);
+            const double dBy_k = dsub(by[e], bym[e]);
+            const double dBx_k = dsub(bx[e], bxm[e]);
+            const double dBz_i = dsub(bz[e], bzl);
+            const double dBy_i = dsub(by[e], byl);
+            const double dBx_j = dsub(bx[e], bxj[e]);
+            if (!PML || (row_main && col_main[e])) {
+                // FDTD.cpp:85-93 / kokkos_functors.h:81-89
+                double tx = dmul(cy, dBz_j), ty = dmul(cz, dBx_k), tz = dmul(cx, dBy_i);
+                if (use_j) {
+                    tx = dadd(dmul(cj, jx[e]), tx);
+                    ty = dadd(dmul(cj, jy[e]), ty);
+                    tz = dadd(dmul(cj, jz[e]), tz);
+                }
+                e_x[e] = dadd(e_x[e], dsub(tx, dmul(cz, dBy_k)));
+                e_y[e] = dadd(e_y[e], dsub(ty, dmul(cx, dBz_i)));
+                e_z[e] = dadd(e_z[e], dsub(tz, dmul(cy, dBx_j)));
+            } else {
+                // FDTD_PML.cpp:113-130
+                syx[e] = round_store<T>(dsub(dmul(syx[e], dcx[e]), dmul(c2x[e], dBz_i)));
+                szx[e] = round_store<T>(dadd(dmul(szx[e], dcx[e]), dmul(c2x[e], dBy_i)));
+                sxy[e] = round_store<T>(dadd(dmul(sxy[e], dcy), dmul(c2y, dBz_j)));
+                szy[e] = round_store<T>(dsub(dmul(szy[e], dcy), dmul(c2y, dBx_j)));
+                sxz[e] = round_store<T>(dsub(dmul(sxz[e], dcz), dmul(c2z, dBy_k)));
+                syz[e] = round_store<T>(dadd(dmul(syz[e], dcz), dmul(c2z, dBx_k)));
+                e_x[e] = dadd(sxz[e], sxy[e]);
+                e_y[e] = dadd(syx[e], syz[e]);
+                e_z[e] = dadd(szy[e], szx[e]);
+            }
+        }
+        stv(Ex + o, e_x, nvalid);
+        stv(Ey + o, e_y, nvalid);
+        stv(Ez + o, e_z, nvalid);
+        if (PML && any_pml) {
+            stv(a.f.SE[S_XY] + o, sxy, nvalid); stv(a.f.SE[S_XZ] + o, sxz, nvalid);
+            stv(a.f.SE[S_YX] + o, syx, nvalid); stv(a.f.SE[S_YZ] + o, syz, nvalid);
+            stv(a.f.SE[S_ZX] + o, szx, nvalid); stv(a.f.SE[S_ZY] + o, szy, nvalid);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) { bxm[e] = bx[e]; bym[e] = by[e]; }
+    }
+}
+
+// ---- small utility kernels ------------------------------------------------------------------------
+
+// Sparse host writes / reads (fdtd_scatter / fdtd_gather): the per-step `get_field(JX)[index] = v`
+// pattern of perf-tests/sample/sample.cpp:66-81.
+template <typename T>
+__global__ void scatter_kernel(T* __restrict__ f, Geom g, const long long* __restrict__ idx,
+                               const T* __restrict__ vals, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long ij = (long long)g.Ni * g.Nj;
+    const long long id = idx[t];
+    const int k = (int)(id / ij) - g.k0;
+    if (k < 0 || k >= g.nk) return;
+    const long long r = id % ij;
+    f[(long long)k * g.plane + (r / g.Ni) * g.pitch + (r % g.Ni)] = vals[t];
+}
+
+template <typename T>
+__global__ void gather_kernel(const T* __restrict__ f, Geom g, const long long* __restrict__ idx,
+                              T* __restrict__ vals, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long ij = (long long)g.Ni * g.Nj;
+    const long long id = idx[t];
+    const int k = (int)(id / ij) - g.k0;
+    if (k < 0 || k >= g.nk) return;
+    const long long r = id % ij;
+    vals[t] = f[(long long)k * g.plane + (r / g.Ni) * g.pitch + (r % g.Ni)];
+}
+
+// Device-resident current source (fdtd_set_source): J = ((amp*wx)*wy)*wz on a box, the product order of
+// perf-tests/sample/sample.cpp:26-31; `zero` writes +0.0 instead (source expired / zeroed_currents on a box).
+struct SourceArgs {
+    int lo[3], hi[3];          // global box
+    const double* w[3];        // device tables, indexed from lo
+    double amp;
+    int zero;
+};
+
+template <typename T>
+__global__ void source_kernel(T* __restrict__ jx, T* __restrict__ jy, T* __restrict__ jz, Geom g, SourceArgs s) {
+    const int ni = s.hi[0] - s.lo[0], nj = s.hi[1] - s.lo[1], nk = s.hi[2] - s.lo[2];
+    const long long total = (long long)ni * nj * nk;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int di = (int)(t % ni), dj = (int)((t / ni) % nj), dk = (int)(t / ((long long)ni * nj));
+        const int k = s.lo[2] + dk - g.k0;
+        if (k < 0 || k >= g.nk) continue;
+        double v = 0.0;
+        if (!s.zero) v = dmul(dmul(dmul(s.amp, s.w[0][di]), s.w[1][dj]), s.w[2][dk]);
+        const long long o = (long long)k * g.plane + (long long)(s.lo[1] + dj) * g.pitch + (s.lo[0] + di);
+        jx[o] = (T)v; jy[o] = (T)v; jz[o] = (T)v;
+    }
+}
+
+}  // namespace fdtd_b200

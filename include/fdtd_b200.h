@@ -1,0 +1,202 @@
+/* ===========================================================================
+ * fdtd_b200.h -- C ABI of libfdtd_b200.so, the B200 (sm_100a) implementation of
+ * the reference's 3-D FDTD Yee leapfrog time step.
+ *
+ * This is the drop-in boundary for the path
+ *     FDTD::update_fields()      (reference src/FDTD/FDTD.cpp:153-157,
+ *                                 src/FDTD_kokkos/FDTD_kokkos.cpp:91-104)
+ *     FDTD_PML::update_fields()  (reference src/FDTD/FDTD_PML.cpp:343-365)
+ * and the calls either side of it (constructor, get_field, zeroed_currents).
+ * The reference has no FFI layer -- its boundary is the C++ class interface
+ * (include/FDTD/FDTD.h:35-40, include/FDTD/FDTD_PML.h:41-44).  The C++ classes
+ * in include/FDTD_b200/ re-expose exactly that interface on top of the entry
+ * points below; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", opaque handle, plain pointers and sizes, no C++/torch types.
+ *   - every call returns an fdtd_status_t; fdtd_last_error() gives the
+ *     thread-local message of the last failing call.
+ *   - host buffers use the reference's dense layout: element (i,j,k) at flat
+ *     index i + j*Ni + k*Ni*Nj (src/FDTD/FDTD.cpp:66-80), element type = the
+ *     solver's dtype (double for FDTD_F64, float for FDTD_F32).
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     FDTD_ERR_CUDA when no sm_100 device is usable.
+ * ===========================================================================*/
+#ifndef FDTD_B200_H_
+#define FDTD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDTD_B200_VERSION 100 /* 0.1.0 */
+
+typedef struct fdtd_solver fdtd_solver_t;
+
+/* Same members, order and types as FDTD_struct::Parameters with FP = double
+ * (reference include/Structures.h:24-38, include/FP.h:3); a Parameters object
+ * may be passed by pointer cast. */
+typedef struct fdtd_params {
+    int Ni, Nj, Nk;
+    double ax, bx, ay, by, az, bz;
+    double dx, dy, dz;
+} fdtd_params_t;
+
+/* Same enumerators and values as FDTD_enums::Component (reference include/Enums.h:5). */
+typedef enum fdtd_component {
+    FDTD_EX = 0, FDTD_EY = 1, FDTD_EZ = 2,
+    FDTD_BX = 3, FDTD_BY = 4, FDTD_BZ = 5,
+    FDTD_JX = 6, FDTD_JY = 7, FDTD_JZ = 8
+} fdtd_component_t;
+
+typedef enum fdtd_dtype {
+    FDTD_F64 = 0, /* FP = double, the reference's only compiling configuration */
+    FDTD_F32 = 1  /* float storage, double arithmetic, one rounding on store */
+} fdtd_dtype_t;
+
+typedef enum fdtd_status {
+    FDTD_OK = 0,
+    FDTD_ERR_INVALID_PARAMETERS = 1, /* std::invalid_argument("ERROR: invalid parameters"), FDTD.cpp:5-7 */
+    FDTD_ERR_INVALID_COMPONENT = 2,  /* std::logic_error("ERROR: Invalid field component"), FDTD.cpp:149 */
+    FDTD_ERR_CUDA = 3,
+    FDTD_ERR_NCCL = 4,
+    FDTD_ERR_STATE = 5,
+    FDTD_ERR_NOMEM = 6,
+    FDTD_ERR_BAD_ARGUMENT = 7
+} fdtd_status_t;
+
+/* fdtd_config_t.flags */
+#define FDTD_FLAG_J_OPENMP_QUIRK 0x1u /* Jx feeds Ex, Ey AND Ez like FDTD_openmp (FDTD.cpp:85,88,91).
+                                         Default is the FDTD_kokkos behaviour (kokkos_functors.h:81-89). */
+#define FDTD_FLAG_NO_FUSION 0x2u      /* force the two-sweep kernels (B sweep, E sweep) instead of the fused pass */
+#define FDTD_FLAG_NO_GRAPH 0x4u       /* never capture fdtd_step(n) into a CUDA graph */
+
+typedef enum fdtd_pml_mode {
+    FDTD_PML_NONE = 0,     /* class FDTD: periodic everywhere */
+    FDTD_PML_PERCENT = 1,  /* class FDTD_PML: thickness_d = int(N_d * pml_percent), FDTD_PML.cpp:254-256 */
+    FDTD_PML_THICKNESS = 2 /* extension: explicit per-axis thickness in cells */
+} fdtd_pml_mode_t;
+
+typedef struct fdtd_config {
+    uint32_t struct_size;   /* = sizeof(fdtd_config_t) */
+    fdtd_params_t grid;     /* GLOBAL grid (all ranks pass the same) */
+    double dt;
+    int32_t dtype;          /* fdtd_dtype_t */
+    uint32_t flags;
+    int32_t pml_mode;       /* fdtd_pml_mode_t */
+    double pml_percent;
+    int32_t pml_thickness[3];
+    int32_t device;         /* CUDA device ordinal; -1 = current device */
+    int32_t rank, nranks;   /* z-slab decomposition, one process per GPU; 0,1 = single GPU */
+} fdtd_config_t;
+
+typedef struct fdtd_info {
+    int32_t Ni, Nj, Nk;        /* global grid */
+    int32_t k_begin, k_end;    /* this rank owns global planes [k_begin, k_end) */
+    int32_t dtype, has_pml;
+    int32_t pml_thickness[3];
+    int64_t pitch;             /* elements per device row (>= Ni, multiple of 128 B) */
+    int64_t plane;             /* elements per device plane = pitch * Nj */
+    int64_t device_bytes;      /* HBM allocated by this solver */
+    int64_t launches;          /* kernels launched by this solver so far */
+    int64_t steps_done;
+    int32_t fused;             /* 1 if fdtd_step uses the fused E+B pass */
+    int32_t rank, nranks, device;
+} fdtd_info_t;
+
+/* ---- life cycle --------------------------------------------------------- */
+
+/* FDTD(Parameters, double dt)  -- reference include/FDTD/FDTD.h:36, src/FDTD/FDTD.cpp:3-61.
+ * fp64, periodic, single GPU (current device), Kokkos J semantics. */
+fdtd_status_t fdtd_create(const fdtd_params_t* params, double dt, fdtd_solver_t** out);
+
+/* FDTD_PML(Parameters, FP dt, FP pml_percent) -- include/FDTD/FDTD_PML.h:42, src/FDTD/FDTD_PML.cpp:205-341. */
+fdtd_status_t fdtd_create_pml(const fdtd_params_t* params, double dt, double pml_percent, fdtd_solver_t** out);
+
+/* Full-control constructor (dtype, J semantics, explicit PML thickness, device, z-slab rank). */
+fdtd_status_t fdtd_create_ex(const fdtd_config_t* cfg, fdtd_solver_t** out);
+
+void fdtd_config_init(fdtd_config_t* cfg); /* zero + defaults (struct_size, device=-1, nranks=1) */
+
+/* ~FDTD() */
+fdtd_status_t fdtd_destroy(fdtd_solver_t* s);
+
+/* ---- the hot path ------------------------------------------------------- */
+
+/* FDTD::update_fields() / FDTD_PML::update_fields(): one Yee step (B half, E, B half).
+ * Asynchronous on the solver's stream; field reads below synchronise as needed. */
+fdtd_status_t fdtd_update_fields(fdtd_solver_t* s);
+
+/* nsteps x update_fields().  Bit-identical to nsteps separate calls. */
+fdtd_status_t fdtd_step(fdtd_solver_t* s, int nsteps);
+
+/* FDTD::zeroed_currents() -- src/FDTD/FDTD.cpp:132-136. */
+fdtd_status_t fdtd_zeroed_currents(fdtd_solver_t* s);
+
+/* ---- field access: what callers do through `Field& get_field(Component)` -- FDTD.cpp:138-151 */
+
+/* Dense copy of this rank's slab (Ni*Nj*(k_end-k_begin) elements of the solver dtype). `count` must
+ * equal that element count.  `host` may be pageable or pinned. */
+fdtd_status_t fdtd_upload(fdtd_solver_t* s, int component, const void* host, size_t count);
+fdtd_status_t fdtd_download(fdtd_solver_t* s, int component, void* host, size_t count);
+
+/* Sparse writes/reads: idx[] are GLOBAL flat indices i + j*Ni + k*Ni*Nj; entries whose plane is not
+ * owned by this rank are skipped on write and left untouched on read.  This is the per-step
+ * `get_field(JX)[index] = value` pattern of perf-tests/sample/sample.cpp:66-81. */
+fdtd_status_t fdtd_scatter(fdtd_solver_t* s, int component, const int64_t* idx, const void* values, size_t n);
+fdtd_status_t fdtd_gather(fdtd_solver_t* s, int component, const int64_t* idx, void* values, size_t n);
+
+/* Device-resident current source (so the sample scenario never crosses PCIe):
+ *   J{x,y,z}(i,j,k) = ((amp[t] * wx[i-lo_i]) * wy[j-lo_j]) * wz[k-lo_k]   on the box [lo, hi)
+ * written before step t (t counted from this call), for t < n_amp.  The product order is the
+ * reference's (sample.cpp:26-31), so host-computed tables reproduce its values bit for bit.
+ * After the last amplitude the solver behaves as if zeroed_currents() had been called
+ * (sample.cpp:84).  Replaces the host loop sample.cpp:66-83 / the "SetCurrent" kernel of
+ * perf-tests/kokkos_sample/kokkos_sample.cpp:91-108. */
+fdtd_status_t fdtd_set_source(fdtd_solver_t* s, const int lo[3], const int hi[3], const double* wx,
+                              const double* wy, const double* wz, const double* amp, int n_amp);
+fdtd_status_t fdtd_clear_source(fdtd_solver_t* s);
+
+/* Apply any deferred work and wait for the device (Kokkos::fence() in kokkos_sample.cpp:110-112). */
+fdtd_status_t fdtd_sync(fdtd_solver_t* s);
+
+/* Zero-copy access for CUDA-aware callers: device pointer to element (0,0,k_begin) of `component`
+ * (row pitch and plane stride in fdtd_info_t).  Flushes deferred work first. */
+fdtd_status_t fdtd_device_ptr(fdtd_solver_t* s, int component, void** dptr);
+
+/* ---- introspection / measurement --------------------------------------- */
+fdtd_status_t fdtd_get_info(fdtd_solver_t* s, fdtd_info_t* info);
+/* CUDA-event stopwatch on the solver's own stream. */
+fdtd_status_t fdtd_timer_start(fdtd_solver_t* s);
+fdtd_status_t fdtd_timer_stop(fdtd_solver_t* s, double* elapsed_ms);
+/* The solver's cudaStream_t (as void*), for callers that want to record their own events. */
+fdtd_status_t fdtd_get_stream(fdtd_solver_t* s, void** stream);
+
+/* ---- multi-GPU: one process per GPU, z-slab ring with one-plane halos ----
+ * (the reference's only distributed design is coarray/fdtd.F90:85-102,149-164) */
+#define FDTD_NCCL_UNIQUE_ID_BYTES 128
+/* Rank 0 calls this and ships the bytes to the other ranks (torch.distributed broadcast, a file, ...). */
+fdtd_status_t fdtd_nccl_unique_id(void* id_out, size_t capacity);
+/* All ranks call this with the same id; uses cfg.rank / cfg.nranks given at creation. */
+fdtd_status_t fdtd_comm_init(fdtd_solver_t* s, const void* id, size_t id_bytes);
+/* Plane range owned by `rank` of `nranks` for a grid with Nk planes (remainder spread over low ranks). */
+void fdtd_slab_range(int Nk, int rank, int nranks, int* k_begin, int* k_end);
+
+/* ---- host-only helpers (no GPU needed) ---------------------------------- */
+/* 1-D PML tables for one axis, from src/FDTD/FDTD_PML.cpp:3-65,98-111,316-338:
+ * sigma[i], decay[i] = exp(-sigma*dt*C), coef2[i] = sigma ? (1-decay)/(sigma*d) : C*dt/d. */
+fdtd_status_t fdtd_pml_profile(int N, int thickness, double d, double dt, double* sigma, double* decay,
+                               double* coef2);
+/* int(N * pml_percent), FDTD_PML.cpp:254-256 */
+int fdtd_pml_thickness(int N, double pml_percent);
+
+const char* fdtd_last_error(void);
+int fdtd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDTD_B200_H_ */

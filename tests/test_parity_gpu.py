@@ -1,0 +1,289 @@
+"""GPU parity: libfdtd_b200.so (through the C ABI) against the CPU oracle and the committed golden
+vectors of the real reference.  Bar (north_star): bit-exact in fp64 and in fp32-storage mode (the
+kernels never contract to FMA); the stated tolerances 1e-12 / 1e-5 relative L-inf are asserted as well.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import C, J_KOKKOS, J_OPENMP, Oracle, run_sample, sample_params, sample_source
+from tests.util import assert_bit_equal, load_both, make_pair, params, rel_linf, seeded_fields
+
+import fdtd_method_b200 as fb
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+
+
+@pytest.mark.parametrize("fusion", [True, False])
+@pytest.mark.parametrize("shape,steps", [((16, 12, 10), 7), ((64, 64, 64), 5), ((32, 8, 4), 9), ((2, 1, 3), 4),
+                                         ((62, 9, 5), 3), ((60, 6, 5), 3), ((128, 20, 40), 4), ((4, 4, 70), 3)])
+def test_periodic_random_bit_exact(shape, steps, fusion):
+    Ni, Nj, Nk = shape
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), fusion=fusion)
+    assert bool(g.info().fused) == fusion
+    load_both(o, g, seeded_fields(11, (Nk, Nj, Ni), same_j=False))
+    o.step(steps)
+    g.step(steps)
+    assert_bit_equal(o, g, what=f"periodic {shape} fusion={fusion}")
+    for c in range(6):
+        assert rel_linf(g.download(c), o.field(c)) <= 1e-12
+
+
+@pytest.mark.parametrize("shape", [(33, 7, 5), (1, 1, 1), (3, 5, 2), (17, 3, 9)])
+def test_periodic_odd_sizes_use_sweeps(shape):
+    """Ni not a multiple of the vector width: the two-sweep kernels take over (still CUDA)."""
+    Ni, Nj, Nk = shape
+    o, g = make_pair(Ni, Nj, Nk)
+    load_both(o, g, seeded_fields(5, (Nk, Nj, Ni), same_j=False))
+    o.step(6)
+    g.step(6)
+    assert_bit_equal(o, g, what=f"odd {shape}")
+
+
+def test_update_fields_one_by_one_equals_step_n():
+    """fdtd_step(n) must be bit-identical to n x update_fields() with reads in between (deferred half step)."""
+    Ni, Nj, Nk = 32, 16, 12
+    o, g = make_pair(Ni, Nj, Nk)
+    f = seeded_fields(3, (Nk, Nj, Ni))
+    load_both(o, g, f)
+    for t in range(5):
+        o.update_fields()
+        g.update_fields()
+        if t % 2 == 0:
+            assert_bit_equal(o, g, what=f"step {t}")   # forces a flush of the pending half step
+    assert_bit_equal(o, g, what="final")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("fusion", [True, False])
+def test_dtype_modes(dtype, fusion):
+    Ni, Nj, Nk = 64, 24, 16
+    o, g = make_pair(Ni, Nj, Nk, dtype=dtype, fusion=fusion)
+    load_both(o, g, seeded_fields(21, (Nk, Nj, Ni), dtype=dtype, same_j=False))
+    o.step(10)
+    g.step(10)
+    assert_bit_equal(o, g, what=f"{dtype} fusion={fusion}")
+    for c in range(6):
+        assert rel_linf(g.download(c), o.field(c)) <= TOL[np.dtype(dtype)]
+
+
+def test_fp32_storage_tracks_fp64_within_tolerance():
+    """north_star: <= 1e-5 relative L-inf in fp32 after N steps (against the fp64 reference semantics)."""
+    n, steps = 32, 100
+    o = Oracle(**sample_params(n))
+    run_sample(o, n, steps)
+    g = fb.FDTD(params(n, n, n), 0.2, dtype=np.float32)
+    lo, hi, active, value = sample_source(n, steps)
+    idx = np.array([i + j * n + k * n * n for k in range(lo[2], hi[2]) for j in range(lo[1], hi[1]) for i in range(lo[0], hi[0])])
+    for t in range(active):
+        vals = np.array([value(t, i % n, (i // n) % n, i // (n * n)) for i in idx], dtype=np.float32)
+        for c in (6, 7, 8):
+            g.scatter(c, idx, vals)
+        g.update_fields()
+    g.zeroed_currents()
+    g.step(steps - active)
+    for c in range(6):
+        assert rel_linf(g.download(c), o.field(c)) <= 1e-5
+
+
+@pytest.mark.parametrize("j_mode", [J_KOKKOS, J_OPENMP])
+@pytest.mark.parametrize("fusion", [True, False])
+def test_current_semantics(j_mode, fusion):
+    """Distinct Jx/Jy/Jz: Kokkos semantics by default, FDTD_openmp's Jx-for-all quirk behind the flag (G1)."""
+    Ni, Nj, Nk = 32, 12, 9
+    o, g = make_pair(Ni, Nj, Nk, j_mode=j_mode, fusion=fusion)
+    load_both(o, g, seeded_fields(8, (Nk, Nj, Ni), same_j=False))
+    o.step(4)
+    g.step(4)
+    assert_bit_equal(o, g, what=f"j_mode={j_mode}")
+
+
+@pytest.mark.parametrize("shape,pml,steps", [((20, 16, 12), 0.2, 10), ((24, 24, 24), 0.13, 6), ((32, 32, 32), 0.2, 12),
+                                            ((33, 10, 10), 0.1, 5), ((16, 16, 16), 0.0, 4), ((8, 8, 8), 0.5, 3)])
+def test_pml_random_bit_exact(shape, pml, steps):
+    Ni, Nj, Nk = shape
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), pml=pml)
+    load_both(o, g, seeded_fields(43, (Nk, Nj, Ni)))
+    for t in range(steps):
+        o.update_fields()
+        g.update_fields()
+        if t == 1:
+            assert_bit_equal(o, g, what=f"pml {shape} step {t}")
+    assert_bit_equal(o, g, what=f"pml {shape}")
+
+
+def test_pml_explicit_thickness_matches_percent():
+    Ni, Nj, Nk = 20, 20, 20
+    o, g = make_pair(Ni, Nj, Nk, pml=0.2, pml_thickness=(4, 4, 4))
+    load_both(o, g, seeded_fields(2, (Nk, Nj, Ni)))
+    o.step(5)
+    g.step(5)
+    assert_bit_equal(o, g, what="pml thickness")
+
+
+@pytest.mark.parametrize("name", ["random_periodic_16x12x10", "random_periodic_33x7x5", "random_pml_20x16x12", "random_pml_24x24x24"])
+def test_golden_random_cases(name, golden_dir):
+    """Committed outputs of the real reference (oracle/make_golden.py) -- no oracle in the loop."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    m = json.loads(str(z["meta"]))
+    Ni, Nj, Nk = m["Ni"], m["Nj"], m["Nk"]
+    p = fb.Parameters(Ni, Nj, Nk, 0, Ni * m["dx"], 0, Nj * m["dy"], 0, Nk * m["dz"], m["dx"], m["dy"], m["dz"])
+    g = fb.FDTD(p, m["dt"], j_openmp_quirk=True) if m["pml_percent"] is None else fb.FDTD_PML(p, m["dt"], m["pml_percent"], j_openmp_quirk=True)
+    f = seeded_fields(m["seed"], (Nk, Nj, Ni))
+    for c in range(9):
+        g.upload(c, f[c])
+    done = 0
+    names = ["EX", "EY", "EZ", "BX", "BY", "BZ"]
+    for s in m["steps"]:
+        g.step(s - done)
+        done = s
+        for c in range(6):
+            assert np.array_equal(g.download(c), z[f"{names[c]}_step{s}"]), f"{name} {names[c]} step {s}"
+
+
+@pytest.mark.parametrize("pml,name", [(None, "sample_32_100_periodic"), (0.2, "sample_32_100_pml02")])
+@pytest.mark.parametrize("device_source", [False, True])
+def test_sample_scenario_golden(pml, name, device_source, golden_dir):
+    """perf-tests/sample/sample.cpp scenario, n=32, 100 steps, against the real reference's fields,
+    with the host per-step J writes (scatter) and with the device-resident source."""
+    n, steps = 32, 100
+    z = np.load(os.path.join(golden_dir, name + "_fields.npz"))
+    p = params(n, n, n)
+    g = fb.FDTD(p, 0.2) if pml is None else fb.FDTD_PML(p, 0.2, pml)
+    lo, hi, active, value = sample_source(n, steps)
+    if device_source:
+        import math
+        PI, T, Tx = 3.14159265358, 8.0, 4.0 * C
+        amp = [math.sin(2.0 * PI * (float(t + 1) * 0.2) / T) for t in range(active)]
+        w = [[math.pow(math.cos(2.0 * PI * (float(i) * C) / Tx), 2.0) for i in range(lo[a], hi[a])] for a in range(3)]
+        g.set_source(lo, hi, w[0], w[1], w[2], amp)
+        g.step(steps)
+    else:
+        idx = np.array([i + j * n + k * n * n for k in range(lo[2], hi[2]) for j in range(lo[1], hi[1]) for i in range(lo[0], hi[0])])
+        for t in range(active):
+            vals = np.array([value(t, i % n, (i // n) % n, i // (n * n)) for i in idx])
+            for c in (6, 7, 8):
+                g.get_field(c)[idx] = vals
+            g.update_fields()
+        g.zeroed_currents()
+        for t in range(active, steps):
+            g.update_fields()
+    for c, nm in enumerate(["EX", "EY", "EZ", "BX", "BY", "BZ"]):
+        assert np.array_equal(g.download(c), z[nm]), f"{name} {nm} device_source={device_source}"
+    # printed 10x10 slice of sample.cpp:125-134 (5 decimals) -- SURVEY.md B.3 row 6
+    if pml is None:
+        ex = g.download(0)
+        row = [f"{v:.5f}" for v in ex[16, 16, 11:21]]
+        assert row == ["0.00373", "-0.02977", "-0.02579", "-0.02357", "-0.02457", "-0.02457", "-0.02357", "-0.02579", "-0.02977", "0.00373"]
+
+
+def test_convergence_unit_tests(golden_dir):
+    """The reference's 12 Convergence.* tests (unit-tests/test_FDTD_method.cpp:71-203) on the GPU solver:
+    ratio in 4.0 +- 0.1, and err_1/err_2 equal to the real reference's to the last bit."""
+    import math
+    gold = json.load(open(os.path.join(golden_dir, "convergence.json")))
+    PI, T = 3.14159265358, 5e-13
+    E_, B_ = {"EX": 0, "EY": 1, "EZ": 2}, {"BX": 3, "BY": 4, "BZ": 5}
+    cases = {
+        "x_axis_EY": (1, 5, 0, 1.0, 1, (16, 8, 4)), "x_axis_BZ": (1, 5, 0, 1.0, 5, (16, 8, 4)),
+        "x_axis_EZ": (2, 4, 0, -1.0, 2, (16, 8, 4)), "x_axis_BY": (2, 4, 0, -1.0, 4, (16, 8, 4)),
+        "y_axis_EX": (0, 5, 1, -1.0, 0, (8, 16, 4)), "y_axis_BZ": (0, 5, 1, -1.0, 5, (8, 16, 4)),
+        "y_axis_EZ": (2, 3, 1, 1.0, 2, (8, 16, 4)), "y_axis_BX": (2, 3, 1, 1.0, 3, (8, 16, 4)),
+        "z_axis_EX": (0, 4, 2, 1.0, 0, (4, 8, 16)), "z_axis_BY": (0, 4, 2, 1.0, 4, (4, 8, 16)),
+        "z_axis_EY": (1, 3, 2, -1.0, 1, (4, 8, 16)), "z_axis_BX": (1, 3, 2, -1.0, 3, (4, 8, 16)),
+    }
+
+    def run(ef, bf, axis, sign, tf, N):
+        Ni, Nj, Nk = N
+        d = (1.0 / float(Ni), 2.0 / float(Nj), 3.0 / float(Nk))
+        box = (0.0, 1.0, 0.0, 2.0, 0.0, 3.0)
+        iters = 16 * (max(N) // 16)
+        dt = T / float(iters)
+        g = fb.FDTD(fb.Parameters(Ni, Nj, Nk, *box, *d), dt)
+        a, b = box[2 * axis], box[2 * axis + 1]
+        e = np.zeros((Nk, Nj, Ni)); bb = np.zeros((Nk, Nj, Ni))
+        for m in range(N[axis]):        # Test_FDTD::initial_filling, src/FDTD/test_FDTD.cpp:5-51
+            x = float(m) * d[axis]
+            sl = [slice(None)] * 3
+            sl[2 - axis] = m
+            e[tuple(sl)] = sign * math.sin(2.0 * PI * (x - a) / (b - a))
+            bb[tuple(sl)] = math.sin(2.0 * PI * (d[axis] / 2.0 + x - a) / (b - a))
+        g.upload(ef, e); g.upload(bf, bb)
+        for _ in range(iters):
+            g.update_fields()
+        f = g.download(tf)
+        is_b = tf > 2                    # Test_FDTD::get_max_abs_error, src/FDTD/test_FDTD.cpp:89-130
+        s, x, err = (1.0 if is_b else sign), (d[axis] / 2.0 if is_b else 0.0), 0.0
+        for m in range(N[axis]):
+            ix = [0, 0, 0]; ix[2 - axis] = m
+            err = max(err, abs(s * f[tuple(ix)] - math.sin(2.0 * PI * (x - a - C * T) / (b - a))))
+            x += d[axis]
+        return err
+
+    for name, (ef, bf, ax, sg, tf, N) in cases.items():
+        e1 = run(ef, bf, ax, sg, tf, N)
+        e2 = run(ef, bf, ax, sg, tf, tuple(2 * v for v in N))
+        assert abs(e1 / e2 - 4.0) <= 0.1, name
+        assert e1 == gold[name]["err1"] and e2 == gold[name]["err2"], name
+
+
+def test_scatter_gather_and_zeroed_currents():
+    Ni, Nj, Nk = 16, 8, 6
+    o, g = make_pair(Ni, Nj, Nk)
+    f = seeded_fields(9, (Nk, Nj, Ni), same_j=False)
+    load_both(o, g, f)
+    idx = np.array([0, 5, Ni * Nj * Nk - 1, 77, 300])
+    for c in range(9):
+        assert np.array_equal(g.get_field(c)[idx], f[c].reshape(-1)[idx])
+    g.get_field(fb.Component.EZ)[idx] = np.arange(5, dtype=np.float64)
+    o.field(2).reshape(-1)[idx] = np.arange(5, dtype=np.float64)
+    o.step(2); g.step(2)
+    assert_bit_equal(o, g, what="after scatter")
+    o.zeroed_currents(); g.zeroed_currents()
+    assert not g.download(6).any() and not g.download(7).any() and not g.download(8).any()
+    o.step(3); g.step(3)
+    assert_bit_equal(o, g, what="after zeroed_currents")
+    assert g.get_field(0).size() == Ni * Nj * Nk
+
+
+def test_errors_match_reference_semantics():
+    with pytest.raises(ValueError, match="invalid parameters"):      # FDTD.cpp:5-7
+        fb.FDTD(params(0, 4, 4), 0.2)
+    with pytest.raises(ValueError, match="invalid parameters"):
+        fb.FDTD(params(4, 4, 4), 0.0)
+    g = fb.FDTD(params(4, 4, 4), 0.2)
+    with pytest.raises(LookupError, match="Invalid field component"):  # FDTD.cpp:149
+        g.get_field(9)
+    with pytest.raises(TypeError):
+        g.upload(0, np.zeros(5))
+
+
+def test_large_grid_properties():
+    """BASELINE size (256^3 fp64, config 1): size-independent properties instead of an oracle run --
+    (a) fused and two-sweep paths agree bit for bit, (b) a uniform field is a fixed point (all curls
+    vanish), (c) linearity: step(a*F) == a*step(F) for a power-of-two scale."""
+    n, steps = 256, 6
+    p = params(n, n, n)
+    rng = np.random.default_rng(42)
+    f = [rng.uniform(-1, 1, size=(n, n, n)) for _ in range(6)]
+    outs = []
+    for fusion, scale in ((True, 1.0), (False, 1.0), (True, 4.0)):
+        g = fb.FDTD(p, 0.2, fusion=fusion)
+        for c in range(6):
+            g.upload(c, f[c] * scale)
+        g.step(steps)
+        outs.append([g.download(c) for c in range(6)])
+        g.close()
+    for c in range(6):
+        assert np.array_equal(outs[0][c], outs[1][c]), "fused vs two-sweep"
+        assert np.array_equal(outs[0][c] * 4.0, outs[2][c]), "linearity"
+    g = fb.FDTD(p, 0.2)
+    for c in range(6):
+        g.upload(c, np.full((n, n, n), float(c + 1)))
+    g.step(3)
+    for c in range(6):
+        assert np.array_equal(g.download(c), np.full((n, n, n), float(c + 1)))
