@@ -1,0 +1,88 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/fdtd_b200.h declares, the
+host-only helpers agree with the oracle, and compute entry points fail loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import C, Oracle
+
+import fdtd_method_b200 as fb
+from fdtd_method_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "fdtd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fdtd_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/fdtd_b200.h but not exported"
+    assert set(names) == set(_capi.SIGNATURES), "python binding table out of sync with the header"
+    assert L.fdtd_version() == 100
+
+
+def test_params_layout_matches_reference_struct():
+    # FDTD_struct::Parameters with FP=double: 3 ints, 4 bytes padding, 9 doubles
+    assert ctypes.sizeof(fb.Parameters) == 88
+    assert fb.Parameters.dx.offset == 64 and fb.Parameters.ax.offset == 16
+    assert [int(c) for c in fb.Component] == list(range(9))
+
+
+@pytest.mark.parametrize("N,pct,d", [(32, 0.2, C), (100, 0.07, 2.5 * C), (16, 0.0, C), (9, 0.5, C), (512, 0.0625, C)])
+def test_pml_profile_matches_oracle(N, pct, d):
+    p = _capi.lib().fdtd_pml_thickness(N, pct)
+    o = Oracle(N, N, N, d, d, d, 0.2, pml_percent=pct)
+    assert p == o.pml_size(0) == int(float(N) * pct)
+    if 2 * p > N:
+        return
+    sigma, decay, coef2 = fb.pml_profile(N, p, d, 0.2)
+    so, do, co = o.pml_tables(0)
+    assert np.array_equal(sigma, so) and np.array_equal(decay, do) and np.array_equal(coef2, co)
+
+
+def test_slab_ranges_tile_the_grid():
+    for Nk in (1, 7, 512, 1000):
+        for P in (1, 2, 3, 8):
+            if P > Nk:
+                continue
+            r = [fb.slab_range(Nk, k, P) for k in range(P)]
+            assert r[0][0] == 0 and r[-1][1] == Nk
+            assert all(r[i][1] == r[i + 1][0] for i in range(P - 1))
+            sizes = [e - b for b, e in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_invalid_parameters_raise_like_the_reference():
+    with pytest.raises(ValueError, match="ERROR: invalid parameters"):
+        fb.FDTD(fb.Parameters(0, 4, 4, 0, 1, 0, 1, 0, 1, 1, 1, 1), 0.1)
+    with pytest.raises(ValueError, match="ERROR: invalid parameters"):
+        fb.FDTD(fb.Parameters(4, 4, 4, 0, 1, 0, 1, 0, 1, 1, 1, 1), -1.0)
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every solver construction must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fb.FDTD(fb.Parameters(4, 4, 4, 0, 1, 0, 1, 0, 1, 1, 1, 1), 0.1)
+
+
+def test_product_never_imports_the_oracle():
+    """The package and bench/product paths must not reference oracle/ (checker only)."""
+    pkg = os.path.join(ROOT, "fdtd_method_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "fdtd_oracle" not in txt, f
