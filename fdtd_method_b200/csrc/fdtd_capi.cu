@@ -120,9 +120,9 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
 // (read on every launch so that tools/sweep.py can walk the table inside one process)
 static int fused_variant() {
     const char* e = std::getenv("FDTD_B200_FUSED_VARIANT");
-    int v = e ? std::atoi(e) : 0;
-    if (v < 0 || v > 5) v = 0;
-    return v;
+    int v = e ? std::atoi(e) : -1;
+    if (v > 11) v = -1;
+    return v;   // -1: per-dtype default
 }
 static int fused_kc_override() {
     const char* e = std::getenv("FDTD_B200_FUSED_KC");
@@ -163,7 +163,9 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
     a.k_lo = k_lo; a.k_hi = k_hi; a.n_half = n_half;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     cudaError_t e;
-    switch (fused_variant()) {
+    int variant = fused_variant();
+    if (variant < 0) variant = (sizeof(T) == 8) ? 5 : 0;   // measured best on B200 (profiles/sweep_r01.md)
+    switch (variant) {
         default:
         case 0: e = launch_fused_variant<T, 8, 1, 2>(s, a); break;
         case 1: e = launch_fused_variant<T, 12, 1, 1>(s, a); break;
@@ -171,6 +173,12 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
         case 3: e = launch_fused_variant<T, 4, 2, 2>(s, a); break;
         case 4: e = launch_fused_variant<T, 10, 1, 2>(s, a); break;
         case 5: e = launch_fused_variant<T, 8, 1, 3>(s, a); break;
+        case 6: e = launch_fused_variant<T, 8, 1, 4>(s, a); break;
+        case 7: e = launch_fused_variant<T, 4, 1, 6>(s, a); break;
+        case 8: e = launch_fused_variant<T, 4, 1, 8>(s, a); break;
+        case 9: e = launch_fused_variant<T, 10, 1, 3>(s, a); break;
+        case 10: e = launch_fused_variant<T, 6, 1, 4>(s, a); break;
+        case 11: e = launch_fused_variant<T, 6, 1, 5>(s, a); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "fused_BE_kernel launch");
     s->launches++;
@@ -671,7 +679,8 @@ fdtd_status_t fdtd_download(fdtd_solver_t* h, int comp, void* host, size_t count
     if ((st = check_component(comp)) != FDTD_OK) return st;
     const size_t expect = (size_t)s->g.Ni * s->g.Nj * s->g.nk;
     if (!host || count != expect) return fail(FDTD_ERR_BAD_ARGUMENT, "download: count must equal Ni*Nj*(k_end-k_begin)");
-    if (comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
+    // only B carries a deferred half step; E(n+1) is already final after the pass
+    if (comp >= BX && comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
     FDTD_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)s->g.Ni * s->esz, s->cur_ptr(comp), (size_t)s->g.pitch * s->esz,
                                     (size_t)s->g.Ni * s->esz, (size_t)s->g.Nj * s->g.nk, cudaMemcpyDeviceToHost, s->stream));
     FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -712,7 +721,7 @@ fdtd_status_t fdtd_gather(fdtd_solver_t* h, int comp, const int64_t* idx, void* 
     const long long total = (long long)s->g.Ni * s->g.Nj * s->g.Nk;
     for (size_t t = 0; t < n; ++t)
         if (idx[t] < 0 || idx[t] >= total) return fail(FDTD_ERR_BAD_ARGUMENT, "gather: index out of range");
-    if (comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
+    if (comp >= BX && comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
     return (s->dtype == FDTD_F32) ? gather_impl<float>(s, comp, idx, values, n) : gather_impl<double>(s, comp, idx, values, n);
 }
 
