@@ -1,0 +1,71 @@
+"""torchrun worker for tests/test_multi_gpu.py: z-slab solvers on WORLD_SIZE GPUs vs the single-domain oracle.
+Exit code 0 = every rank bit-identical to its slab of the oracle's fields."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import fdtd_method_b200 as fb  # noqa: E402
+from fdtd_method_b200.slab import create_distributed  # noqa: E402
+from oracle.pyoracle import C, J_KOKKOS, Oracle  # noqa: E402
+from tests.util import params, seeded_fields  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cases = [
+        # (shape, pml, fusion, dtype, steps)
+        ((16, 12, 10), None, True, np.float64, 7),
+        ((16, 12, 10), None, False, np.float64, 7),
+        ((32, 20, 2 * world), None, True, np.float64, 5),      # slabs of 2 planes
+        ((32, 20, world), None, True, np.float64, 4),          # slabs of 1 plane
+        ((64, 40, 33), None, True, np.float32, 6),
+        ((20, 16, 24), 0.2, False, np.float64, 8),
+        ((33, 9, 11), None, True, np.float64, 5),              # odd Ni -> two-sweep kernels
+    ]
+    failures = 0
+    for shape, pml, fusion, dtype, steps in cases:
+        Ni, Nj, Nk = shape
+        d = (C, 1.25 * C, 0.8 * C)
+        p = params(Ni, Nj, Nk, *d)
+        if pml is None:
+            g = create_distributed(fb.FDTD, p, 0.2, dtype=dtype, fusion=fusion)
+        else:
+            g = create_distributed(fb.FDTD_PML, p, 0.2, pml, dtype=dtype, fusion=fusion)
+        o = Oracle(Ni, Nj, Nk, d[0], d[1], d[2], 0.2, dtype=dtype, j_mode=J_KOKKOS, pml_percent=pml)
+        f = seeded_fields(23, (Nk, Nj, Ni), dtype=dtype, same_j=False)
+        kb, ke = g.k_begin, g.k_end
+        for c in range(9):
+            o.field(c)[...] = f[c]
+            g.upload(c, f[c][kb:ke])
+        for t in range(steps):
+            o.update_fields()
+            g.update_fields()
+            if t == 1:   # mid-run read forces the deferred half step + ghost refresh path
+                for c in range(6):
+                    if not np.array_equal(g.download(c), o.field(c)[kb:ke]):
+                        failures += 1
+                        print(f"[rank {rank}] MISMATCH mid-run {shape} pml={pml} fusion={fusion} comp {c}", flush=True)
+        for c in range(6):
+            if not np.array_equal(g.download(c), o.field(c)[kb:ke]):
+                failures += 1
+                print(f"[rank {rank}] MISMATCH {shape} pml={pml} fusion={fusion} {np.dtype(dtype).name} comp {c}", flush=True)
+        g.close()
+    t = torch.tensor([failures], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"mgpu_worker: world={world} total mismatches={int(t[0])}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if int(t[0]) else 0)
+
+
+if __name__ == "__main__":
+    main()
