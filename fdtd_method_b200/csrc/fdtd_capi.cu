@@ -14,6 +14,7 @@
 #include <string>
 
 #include "fused_kernel.cuh"
+#include "fused_kernel_v2.cuh"
 #include "solver.h"
 #include "sweep_kernels.cuh"
 
@@ -98,19 +99,42 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
     a.k_lo = 0; a.k_hi = s->g.nk;
     a.n_half = n_half; a.do_pml = do_pml;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
+    a.mode = 0;
+    for (int d = 0; d < 3; ++d) { a.ib_lo[d] = 0; a.ib_hi[d] = 0; }
     dim3 block(SWEEP_BX, SWEEP_BY);
     const int gx = (s->g.Ni + SWEEP_BX * V - 1) / (SWEEP_BX * V);
     const int gy = (s->g.Nj + SWEEP_BY - 1) / SWEEP_BY;
     a.kc = pick_kc(s, gx * gy, s->g.nk);
     const int gz = (s->g.nk + a.kc - 1) / a.kc;
     dim3 grid(gx, gy, gz);
-    if (is_B) {
-        if (s->has_pml) sweep_B_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
-        else sweep_B_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
-    } else {
-        if (s->has_pml) sweep_E_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
+    if (!s->has_pml) {
+        if (is_B) sweep_B_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
         else sweep_E_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
+        FDTD_CUDA_TRY(cudaGetLastError());
+        s->launches++;
+        return FDTD_OK;
     }
+    // PML solver: the interior (main box, i bounds aligned inward to the vector width) runs the lean PML=false
+    // instantiation, the shell (and the unaligned fringe of the main box) the PML=true one.  Disjoint cell sets,
+    // same arithmetic per cell as the single launch (order inside a phase is irrelevant).
+    for (int d = 0; d < 3; ++d) { a.ib_lo[d] = s->main_lo[d]; a.ib_hi[d] = s->main_hi[d]; }
+    a.ib_lo[0] = (a.ib_lo[0] + V - 1) / V * V;
+    a.ib_hi[0] = a.ib_hi[0] / V * V;
+    const long long inner = (long long)(a.ib_hi[0] - a.ib_lo[0]) * (a.ib_hi[1] - a.ib_lo[1]) * (a.ib_hi[2] - a.ib_lo[2]);
+    const bool split = a.ib_hi[0] > a.ib_lo[0] && a.ib_hi[1] > a.ib_lo[1] && a.ib_hi[2] > a.ib_lo[2] &&
+                       inner >= (1 << 15) && !(s->cfg.flags & FDTD_FLAG_NO_PML_SPLIT);
+    if (split) {
+        a.mode = 1;
+        if (is_B) sweep_B_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
+        else sweep_E_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
+        FDTD_CUDA_TRY(cudaGetLastError());
+        s->launches++;
+        a.mode = 2;
+        const bool fringe = (a.ib_lo[0] != s->main_lo[0]) || (a.ib_hi[0] != s->main_hi[0]);
+        if (is_B && !do_pml && !fringe) return FDTD_OK;   // deferred half step: nothing left outside the inner box
+    }
+    if (is_B) sweep_B_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
+    else sweep_E_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
     FDTD_CUDA_TRY(cudaGetLastError());
     s->launches++;
     return FDTD_OK;
@@ -121,7 +145,7 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
 static int fused_variant() {
     const char* e = std::getenv("FDTD_B200_FUSED_VARIANT");
     int v = e ? std::atoi(e) : -1;
-    if (v > 11) v = -1;
+    if (v > 40) v = -1;
     return v;   // -1: per-dtype default
 }
 static int fused_kc_override() {
@@ -146,6 +170,33 @@ static cudaError_t launch_fused_variant(Solver* s, FusedArgs<T>& a) {
     a.kc = kc;
     const int gz = (np + kc - 1) / kc;
     fused_BE_kernel<T, BY, RJ, MINB><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), 0, s->stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T, int BY, int PF, int D, int MINB>
+static cudaError_t launch_fused2_variant(Solver* s, FusedArgs<T>& a) {
+    constexpr int V = VecOf<T>::V;
+    constexpr int TIU = FUSED_OUT_LANES * V;
+    constexpr int TJU = BY - 2;
+    constexpr size_t smem = fused2_smem_bytes<BY, PF, D>();
+    static bool configured[16] = {};
+    if (!configured[s->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(fused_BE2_kernel<T, BY, PF, D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[s->device & 15] = true;
+    }
+    const int gx = (s->g.Ni + TIU - 1) / TIU;
+    const int gy = (s->g.Nj + TJU - 1) / TJU;
+    const int np = a.k_hi - a.k_lo;
+    int kc = fused_kc_override();
+    if (kc <= 0) {
+        kc = 64;
+        while (kc > 8 && (long long)gx * gy * ((np + kc - 1) / kc) < 148 * 6) kc /= 2;
+    }
+    if (kc > np) kc = np;
+    a.kc = kc;
+    const int gz = (np + kc - 1) / kc;
+    fused_BE2_kernel<T, BY, PF, D, MINB><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -179,6 +230,18 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
         case 9: e = launch_fused_variant<T, 10, 1, 3>(s, a); break;
         case 10: e = launch_fused_variant<T, 6, 1, 4>(s, a); break;
         case 11: e = launch_fused_variant<T, 6, 1, 5>(s, a); break;
+        // v2: <BY, PF (1 = register prefetch, 2 = cp.async ring), ring depth, min CTAs/SM>
+        case 20: e = launch_fused2_variant<T, 8, 1, 1, 2>(s, a); break;
+        case 21: e = launch_fused2_variant<T, 8, 1, 1, 3>(s, a); break;
+        case 22: e = launch_fused2_variant<T, 8, 2, 2, 2>(s, a); break;
+        case 23: e = launch_fused2_variant<T, 8, 2, 3, 2>(s, a); break;
+        case 24: e = launch_fused2_variant<T, 10, 2, 2, 2>(s, a); break;
+        case 25: e = launch_fused2_variant<T, 16, 2, 2, 1>(s, a); break;
+        case 26: e = launch_fused2_variant<T, 12, 2, 3, 1>(s, a); break;
+        case 27: e = launch_fused2_variant<T, 8, 0, 1, 3>(s, a); break;
+        case 28: e = launch_fused2_variant<T, 16, 1, 1, 1>(s, a); break;
+        case 29: e = launch_fused2_variant<T, 12, 1, 1, 2>(s, a); break;
+        case 30: e = launch_fused2_variant<T, 8, 2, 4, 1>(s, a); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "fused_BE_kernel launch");
     s->launches++;
@@ -238,7 +301,7 @@ static fdtd_status_t exchange_B_bottom(Solver* s) {
 }
 
 // Everything the fused pass needs: bottom ghost of Bx,By,Ex,Ey,Ez (to rebuild B'(-1)) and top ghost of Ex,Ey.
-static fdtd_status_t exchange_fused(Solver* s) {
+static fdtd_status_t exchange_fused(Solver* s, cudaStream_t stream) {
     if (s->cfg.nranks <= 1 || s->ghosts_fused_valid) return FDTD_OK;
     const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
     const size_t bytes = (size_t)s->g.plane * s->esz;
@@ -249,7 +312,7 @@ static fdtd_status_t exchange_fused(Solver* s) {
         x[n++] = PlaneXfer{plane_ptr(s, up_comps[c], s->cur, s->g.nk - 1), up, plane_ptr(s, up_comps[c], s->cur, -1), down, bytes};
     for (int c = 0; c < 2; ++c)
         x[n++] = PlaneXfer{plane_ptr(s, EX + c, s->cur, 0), down, plane_ptr(s, EX + c, s->cur, s->g.nk), up, bytes};
-    fdtd_status_t st = nccl_exchange(s, x, n, s->stream);
+    fdtd_status_t st = nccl_exchange(s, x, n, stream);
     if (st == FDTD_OK) { s->ghosts_fused_valid = true; s->ghosts_e_valid = true; s->ghosts_b_valid = true; }
     return st;
 }
@@ -331,10 +394,29 @@ static fdtd_status_t advance_one(Solver* s) {
     }
     const int n_half = s->b_pending ? 2 : 1;
     if (s->fused) {
-        st = exchange_fused(s);
-        if (st != FDTD_OK) return st;
-        st = DISPATCH(s, launch_fused, s, n_half, 0, s->g.nk);
-        if (st != FDTD_OK) return st;
+        const int H = 8;   // boundary depth (planes) computed after the halo has landed
+        if (s->cfg.nranks > 1 && !s->ghosts_fused_valid && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP)) {
+            // north_star (d): halo exchange on its own stream, overlapped with the interior chunks.
+            //   comm stream   : wait(previous work) -> 7-plane ring exchange into the ghost planes -> ev_b
+            //   compute stream: interior planes [H, nk-H) (never touch a ghost) -> wait(ev_b) -> the two boundary slabs
+            FDTD_CUDA_TRY(cudaEventRecord(s->ev_a, s->stream));
+            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
+            st = exchange_fused(s, s->comm_stream);
+            if (st != FDTD_OK) return st;
+            FDTD_CUDA_TRY(cudaEventRecord(s->ev_b, s->comm_stream));
+            st = DISPATCH(s, launch_fused, s, n_half, H, s->g.nk - H);
+            if (st != FDTD_OK) return st;
+            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
+            st = DISPATCH(s, launch_fused, s, n_half, 0, H);
+            if (st != FDTD_OK) return st;
+            st = DISPATCH(s, launch_fused, s, n_half, s->g.nk - H, s->g.nk);
+            if (st != FDTD_OK) return st;
+        } else {
+            st = exchange_fused(s, s->stream);
+            if (st != FDTD_OK) return st;
+            st = DISPATCH(s, launch_fused, s, n_half, 0, s->g.nk);
+            if (st != FDTD_OK) return st;
+        }
         s->cur ^= 1;
     } else {
         st = exchange_E_top(s);

@@ -40,6 +40,11 @@ struct SweepArgs {
     int n_half;         // B sweep: 1 or 2 half steps on main cells (0: leave main cells untouched)
     int do_pml;         // B sweep: also advance the PML shell (full step)
     int j_quirk;        // E sweep: FDTD_openmp semantics, Jx feeds all three components
+    // PML solvers split every sweep into two launches so that the (large) interior runs the lean PML=false
+    // instantiation at full occupancy: mode 1 = only cells inside the inner box `ib` (the main box with its
+    // i bounds aligned inward to the vector width), mode 2 = only cells outside it, mode 0 = every cell.
+    int mode;
+    int ib_lo[3], ib_hi[3];   // inner box, GLOBAL coordinates
 };
 
 constexpr int SWEEP_BX = 32;  // lanes along i
@@ -52,8 +57,14 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
     const int i0 = (blockIdx.x * SWEEP_BX + threadIdx.x) * V;
     const int j = blockIdx.y * SWEEP_BY + threadIdx.y;
     if (i0 >= Ni || j >= Nj) return;
-    const int kb = a.k_lo + blockIdx.z * a.kc;
-    const int ke = min(kb + a.kc, a.k_hi);
+    int kb = a.k_lo + blockIdx.z * a.kc;
+    int ke = min(kb + a.kc, a.k_hi);
+    const bool in_ij = (a.mode != 0) && (i0 >= a.ib_lo[0]) && (i0 + V <= a.ib_hi[0]) && (j >= a.ib_lo[1]) && (j < a.ib_hi[1]);
+    if (a.mode == 1) {
+        if (!in_ij) return;
+        kb = max(kb, a.ib_lo[2] - a.g.k0);
+        ke = min(ke, a.ib_hi[2] - a.g.k0);
+    }
     if (kb >= ke) return;
 
     const int nvalid = min(V, Ni - i0);
@@ -97,12 +108,22 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
         ldv(Ex + o, ex);
         ldv(Ey + o, ey);
     }
+    bool carry_ok = true;
     for (int k = kb; k < ke; ++k) {
         int kn = k + 1;
         if (kn == a.g.nk && a.g.wrap_k) kn = 0;
         const long long pk = (long long)k * a.g.plane;
         const long long pkn = (long long)kn * a.g.plane;
         const long long o = pk + row + i0;
+        if (a.mode == 2 && in_ij && (a.g.k0 + k >= a.ib_lo[2]) && (a.g.k0 + k < a.ib_hi[2])) {
+            carry_ok = false;      // this cell belongs to the mode-1 launch
+            continue;
+        }
+        if (!carry_ok) {
+            ldv(Ex + o, ex);
+            ldv(Ey + o, ey);
+            carry_ok = true;
+        }
 
         double exn[V], eyn[V], ez[V], ezj[V], exj[V], bx[V], by[V], bz[V];
         ldv(Ex + pkn + row + i0, exn);
@@ -197,8 +218,14 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
     const int i0 = (blockIdx.x * SWEEP_BX + threadIdx.x) * V;
     const int j = blockIdx.y * SWEEP_BY + threadIdx.y;
     if (i0 >= Ni || j >= Nj) return;
-    const int kb = a.k_lo + blockIdx.z * a.kc;
-    const int ke = min(kb + a.kc, a.k_hi);
+    int kb = a.k_lo + blockIdx.z * a.kc;
+    int ke = min(kb + a.kc, a.k_hi);
+    const bool in_ij = (a.mode != 0) && (i0 >= a.ib_lo[0]) && (i0 + V <= a.ib_hi[0]) && (j >= a.ib_lo[1]) && (j < a.ib_hi[1]);
+    if (a.mode == 1) {
+        if (!in_ij) return;
+        kb = max(kb, a.ib_lo[2] - a.g.k0);
+        ke = min(ke, a.ib_hi[2] - a.g.k0);
+    }
     if (kb >= ke) return;
 
     const int nvalid = min(V, Ni - i0);
@@ -250,10 +277,23 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
         ldv(Bx + o, bxm);
         ldv(By + o, bym);
     }
+    bool carry_ok = true;
     for (int k = kb; k < ke; ++k) {
         const long long pk = (long long)k * a.g.plane;
         const long long o = pk + row + i0;
         const int kg = a.g.k0 + k;
+        if (a.mode == 2 && in_ij && (kg >= a.ib_lo[2]) && (kg < a.ib_hi[2])) {
+            carry_ok = false;      // this cell belongs to the mode-1 launch
+            continue;
+        }
+        if (!carry_ok) {
+            int km = k - 1;
+            if (km < 0 && a.g.wrap_k) km = a.g.nk - 1;
+            const long long om = (long long)km * a.g.plane + row + i0;
+            ldv(Bx + om, bxm);
+            ldv(By + om, bym);
+            carry_ok = true;
+        }
 
         double bx[V], by[V], bz[V], bzj[V], bxj[V], e_x[V], e_y[V], e_z[V];
         ldv(Bx + o, bx);

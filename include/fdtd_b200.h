@@ -73,6 +73,8 @@ typedef enum fdtd_status {
                                          Default is the FDTD_kokkos behaviour (kokkos_functors.h:81-89). */
 #define FDTD_FLAG_NO_FUSION 0x2u      /* force the two-sweep kernels (B sweep, E sweep) instead of the fused pass */
 #define FDTD_FLAG_NO_GRAPH 0x4u       /* never capture fdtd_step(n) into a CUDA graph */
+#define FDTD_FLAG_NO_OVERLAP 0x8u     /* multi-GPU: issue the halo exchange on the compute stream (no overlap) */
+#define FDTD_FLAG_NO_PML_SPLIT 0x10u  /* PML: one launch per sweep with a per-cell predicate instead of interior + shell launches */
 
 typedef enum fdtd_pml_mode {
     FDTD_PML_NONE = 0,     /* class FDTD: periodic everywhere */

@@ -30,6 +30,8 @@ def main():
         ((64, 40, 33), None, True, np.float32, 6),
         ((20, 16, 24), 0.2, False, np.float64, 8),
         ((33, 9, 11), None, True, np.float64, 5),              # odd Ni -> two-sweep kernels
+        ((32, 16, 32 * world), None, True, np.float64, 5),     # 32 planes per rank: overlapped halo exchange path
+        ((64, 48, 40 * world), 0.1, False, np.float64, 5),     # PML interior/shell split on slabs
     ]
     failures = 0
     for shape, pml, fusion, dtype, steps in cases:

@@ -116,6 +116,23 @@ def test_pml_random_bit_exact(shape, pml, steps):
     assert_bit_equal(o, g, what=f"pml {shape}")
 
 
+@pytest.mark.parametrize("pml_split", [True, False])
+@pytest.mark.parametrize("shape,pml,dtype", [((64, 48, 48), 0.1, np.float64), ((50, 44, 44), 0.1, np.float64),
+                                             ((52, 44, 44), 0.1, np.float32), ((64, 40, 72), 0.07, np.float64)])
+def test_pml_interior_shell_split(shape, pml, dtype, pml_split):
+    """Grids large enough for the two-launch PML path (lean kernel on the aligned interior box, PML kernel on
+    the shell and the unaligned fringe) -- must equal the oracle and the single-launch path bit for bit."""
+    Ni, Nj, Nk = shape
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), pml=pml, dtype=dtype, pml_split=pml_split)
+    load_both(o, g, seeded_fields(77, (Nk, Nj, Ni), dtype=dtype, same_j=False))
+    for t in range(6):
+        o.update_fields()
+        g.update_fields()
+        if t == 2:
+            assert_bit_equal(o, g, what=f"pml split={pml_split} {shape} mid-run (flush path)")
+    assert_bit_equal(o, g, what=f"pml split={pml_split} {shape}")
+
+
 def test_pml_explicit_thickness_matches_percent():
     Ni, Nj, Nk = 20, 20, 20
     o, g = make_pair(Ni, Nj, Nk, pml=0.2, pml_thickness=(4, 4, 4))
