@@ -17,6 +17,7 @@ F64, F32 = 0, 1
 PML_NONE, PML_PERCENT, PML_THICKNESS = 0, 1, 2
 FLAG_J_OPENMP_QUIRK, FLAG_NO_FUSION, FLAG_NO_GRAPH, FLAG_NO_OVERLAP = 0x1, 0x2, 0x4, 0x8
 FLAG_NO_PML_SPLIT = 0x10
+FLAG_NO_TEMPORAL = 0x20
 NCCL_UNIQUE_ID_BYTES = 128
 
 OK, ERR_INVALID_PARAMETERS, ERR_INVALID_COMPONENT, ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_NOMEM, ERR_BAD_ARGUMENT = range(8)

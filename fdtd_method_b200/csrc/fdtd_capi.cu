@@ -15,6 +15,7 @@
 
 #include "fused_kernel.cuh"
 #include "fused_kernel_v2.cuh"
+#include "fused_kernel_t2.cuh"
 #include "solver.h"
 #include "sweep_kernels.cuh"
 
@@ -248,6 +249,77 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
     return FDTD_OK;
 }
 
+// ---- temporally blocked pass: two Yee steps per launch (fused_kernel_t2.cuh) -------------------------------
+// Variant table <BY rows per CTA, ring depth D, min CTAs/SM>; FDTD_B200_T2_VARIANT picks one.
+static int t2_variant() {
+    const char* e = std::getenv("FDTD_B200_T2_VARIANT");
+    return e ? std::atoi(e) : -1;
+}
+
+template <typename T, int BY, int D, int MINB>
+static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
+    constexpr int V = VecOf<T>::V;
+    constexpr int TIU = FUSED_OUT_LANES * V;
+    constexpr int TJU = BY - 4;
+    constexpr size_t smem = fused_t2_smem_bytes<BY, D>();
+    static bool configured[16] = {};
+    if (!configured[s->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[s->device & 15] = true;
+    }
+    const int gx = (s->g.Ni + TIU - 1) / TIU;
+    const int gy = (s->g.Nj + TJU - 1) / TJU;
+    const int np = a.k_hi - a.k_lo;
+    int kc = fused_kc_override();
+    if (kc <= 0) {
+        // 3 redundant plane iterations per chunk: keep chunks long, but leave enough CTAs for ~8 waves
+        kc = 128;
+        while (kc > 16 && (long long)gx * gy * ((np + kc - 1) / kc) < 148LL * MINB * 8) kc /= 2;
+    }
+    if (kc > np) kc = np;
+    a.kc = kc;
+    const int gz = (np + kc - 1) / kc;
+    fused_BE_T2_kernel<T, BY, D, MINB><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int src2, double amp2) {
+    FusedT2Args<T> a;
+    a.g = s->g; a.c = s->c; a.jbox = s->jbox;
+    for (int c = 0; c < 3; ++c) {
+        a.Ein[c] = static_cast<const T*>(s->p[EX + c][s->cur]);
+        a.Bin[c] = static_cast<const T*>(s->p[BX + c][s->cur]);
+        a.Eout[c] = static_cast<T*>(s->p[EX + c][s->cur ^ 1]);
+        a.Bout[c] = static_cast<T*>(s->p[BX + c][s->cur ^ 1]);
+        a.J[c] = static_cast<const T*>(s->p[JX + c][0]);
+        a.s_lo[c] = s->src_lo[c]; a.s_hi[c] = s->src_hi[c]; a.sw[c] = s->d_w[c];
+    }
+    a.k_lo = k_lo; a.k_hi = k_hi; a.n_half = n_half;
+    a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
+    a.src2 = src2; a.amp2 = amp2;
+    cudaError_t e;
+    int variant = t2_variant();
+    if (variant < 0) variant = 0;
+    switch (variant) {
+        default:
+        case 0: e = launch_t2_variant<T, 8, 3, 2>(s, a); break;
+        case 1: e = launch_t2_variant<T, 8, 2, 2>(s, a); break;
+        case 2: e = launch_t2_variant<T, 10, 2, 2>(s, a); break;
+        case 3: e = launch_t2_variant<T, 12, 3, 1>(s, a); break;
+        case 4: e = launch_t2_variant<T, 16, 3, 1>(s, a); break;
+        case 5: e = launch_t2_variant<T, 16, 2, 1>(s, a); break;
+        case 6: e = launch_t2_variant<T, 12, 4, 1>(s, a); break;
+        case 7: e = launch_t2_variant<T, 8, 4, 1>(s, a); break;
+        case 8: e = launch_t2_variant<T, 6, 3, 3>(s, a); break;
+        case 9: e = launch_t2_variant<T, 14, 3, 1>(s, a); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "fused_BE_T2_kernel launch");
+    s->launches++;
+    return FDTD_OK;
+}
+
 template <typename T>
 static fdtd_status_t launch_source(Solver* s, double amp, int zero) {
     SourceArgs sa;
@@ -317,8 +389,35 @@ static fdtd_status_t exchange_fused(Solver* s, cudaStream_t stream) {
     return st;
 }
 
+// Everything the T2 pass needs: two bottom ghost planes of E, B (to rebuild B1(-2), B1(-1), E1(-1)) plus J(-1),
+// top ghost plane nk of E, B, J (B1(nk), E1(nk)) and top ghost plane nk+1 of Ex, Ey.  J travels because stage A
+// re-computes the neighbour's boundary plane, current term included.
+static fdtd_status_t exchange_t2(Solver* s, cudaStream_t stream) {
+    if (s->cfg.nranks <= 1 || s->ghosts_t2_valid) return FDTD_OK;
+    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
+    const size_t bytes = (size_t)s->g.plane * s->esz;
+    const int nk = s->g.nk;
+    PlaneXfer x[32];
+    int n = 0;
+    auto gen = [&](int c) { return c < JX ? s->cur : 0; };
+    // to the upper neighbour: our top planes nk-2, nk-1 become its planes -2, -1
+    for (int c = EX; c <= BZ; ++c)
+        for (int d = 1; d <= 2; ++d)
+            x[n++] = PlaneXfer{plane_ptr(s, c, gen(c), nk - d), up, plane_ptr(s, c, gen(c), -d), down, bytes};
+    for (int c = JX; c <= JZ; ++c)
+        x[n++] = PlaneXfer{plane_ptr(s, c, 0, nk - 1), up, plane_ptr(s, c, 0, -1), down, bytes};
+    // to the lower neighbour: our bottom plane 0 becomes its plane nk (E, B, J), our plane 1 its plane nk+1 (Ex, Ey)
+    for (int c = EX; c <= JZ; ++c)
+        x[n++] = PlaneXfer{plane_ptr(s, c, gen(c), 0), down, plane_ptr(s, c, gen(c), nk), up, bytes};
+    for (int c = EX; c <= EY; ++c)
+        x[n++] = PlaneXfer{plane_ptr(s, c, s->cur, 1), down, plane_ptr(s, c, s->cur, nk + 1), up, bytes};
+    fdtd_status_t st = nccl_exchange(s, x, n, stream);
+    if (st == FDTD_OK) { s->ghosts_t2_valid = true; s->ghosts_fused_valid = true; s->ghosts_e_valid = true; s->ghosts_b_valid = true; }
+    return st;
+}
+
 static void invalidate_ghosts(Solver* s) {
-    s->ghosts_e_valid = s->ghosts_b_valid = s->ghosts_fused_valid = false;
+    s->ghosts_e_valid = s->ghosts_b_valid = s->ghosts_fused_valid = s->ghosts_t2_valid = false;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -370,15 +469,54 @@ static fdtd_status_t zero_currents_impl(Solver* s) {
         for (int a = 0; a < 3; ++a) { s->src_lo[a] = lo[a]; s->src_hi[a] = hi[a]; }
         if (st != FDTD_OK) return st;
     } else {
-        const size_t bytes = (size_t)s->g.plane * (size_t)(s->g.nk + 2) * s->esz;
+        const size_t bytes = (size_t)s->g.plane * (size_t)(s->g.nk + 2 * GHOST_PLANES) * s->esz;
         for (int c = JX; c <= JZ; ++c) FDTD_CUDA_TRY(cudaMemsetAsync(s->base[c][0], 0, bytes, s->stream));
     }
     jbox_clear(s);
     return FDTD_OK;
 }
 
-static fdtd_status_t advance_one(Solver* s) {
+// The J arrays lag the device-resident source by one step after a T2 pass that evaluated the second step's
+// source in the kernel: write that step's values now (anything that reads J, or the end of fdtd_step()).
+static fdtd_status_t materialize_J(Solver* s) {
+    if (!s->j_stale) return FDTD_OK;
+    s->j_stale = false;
+    if (s->src_t < 1 || s->src_t > (int)s->src_amp.size()) return FDTD_OK;
+    return DISPATCH(s, launch_source, s, s->src_amp[s->src_t - 1], 0);
+}
+
+static bool t2_disabled_by_env() {
+    const char* e = std::getenv("FDTD_B200_NO_T2");
+    return e && std::atoi(e) != 0;
+}
+
+// One launch group over the slab with the halo exchange overlapped: interior planes [H, nk-H) never touch a ghost
+// plane and run while the ring exchange is in flight on the comm stream; the two boundary slabs follow.
+template <typename LaunchFn, typename ExchangeFn>
+static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, LaunchFn launch, ExchangeFn exchange) {
+    const int H = 8;   // boundary depth (planes) computed after the halo has landed
     fdtd_status_t st;
+    if (s->cfg.nranks > 1 && !ghosts_valid && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP)) {
+        // north_star (d): halo exchange on its own stream, overlapped with the interior chunks.
+        //   comm stream   : wait(previous work) -> ring exchange into the ghost planes -> ev_b
+        //   compute stream: interior planes [H, nk-H) -> wait(ev_b) -> the two boundary slabs
+        FDTD_CUDA_TRY(cudaEventRecord(s->ev_a, s->stream));
+        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
+        if ((st = exchange(s->comm_stream)) != FDTD_OK) return st;
+        FDTD_CUDA_TRY(cudaEventRecord(s->ev_b, s->comm_stream));
+        if ((st = launch(H, s->g.nk - H)) != FDTD_OK) return st;
+        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
+        if ((st = launch(0, H)) != FDTD_OK) return st;
+        return launch(s->g.nk - H, s->g.nk);
+    }
+    if ((st = exchange(s->stream)) != FDTD_OK) return st;
+    return launch(0, s->g.nk);
+}
+
+// Advance by one step, or by two when the temporally blocked pass applies; *done = steps advanced.
+static fdtd_status_t advance(Solver* s, int remaining, int* done) {
+    fdtd_status_t st;
+    *done = 1;
     // device-resident source: write J for this step (kokkos_sample.cpp:91-108), or retire it (sample.cpp:84)
     if (s->src_active) {
         if (s->src_t < (int)s->src_amp.size()) {
@@ -386,35 +524,31 @@ static fdtd_status_t advance_one(Solver* s) {
             if (st != FDTD_OK) return st;
             jbox_union(s, s->src_lo, s->src_hi);
             s->src_t++;
+            s->j_stale = false;
         } else {
             s->src_active = false;
+            s->j_stale = false;
             st = zero_currents_impl(s);
             if (st != FDTD_OK) return st;
         }
     }
     const int n_half = s->b_pending ? 2 : 1;
     if (s->fused) {
-        const int H = 8;   // boundary depth (planes) computed after the halo has landed
-        if (s->cfg.nranks > 1 && !s->ghosts_fused_valid && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP)) {
-            // north_star (d): halo exchange on its own stream, overlapped with the interior chunks.
-            //   comm stream   : wait(previous work) -> 7-plane ring exchange into the ghost planes -> ev_b
-            //   compute stream: interior planes [H, nk-H) (never touch a ghost) -> wait(ev_b) -> the two boundary slabs
-            FDTD_CUDA_TRY(cudaEventRecord(s->ev_a, s->stream));
-            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
-            st = exchange_fused(s, s->comm_stream);
+        // Pair this step with the next one unless the source retires in between (J would have to change to zero).
+        const bool src_ends = s->src_active && s->src_t >= (int)s->src_amp.size();
+        if (s->t2 && remaining >= 2 && !src_ends && !t2_disabled_by_env()) {
+            const int src2 = s->src_active ? 1 : 0;
+            const double amp2 = src2 ? s->src_amp[s->src_t] : 0.0;
+            st = overlapped(s, s->ghosts_t2_valid,
+                            [&](int lo, int hi) { return DISPATCH(s, launch_t2, s, n_half, lo, hi, src2, amp2); },
+                            [&](cudaStream_t q) { return exchange_t2(s, q); });
             if (st != FDTD_OK) return st;
-            FDTD_CUDA_TRY(cudaEventRecord(s->ev_b, s->comm_stream));
-            st = DISPATCH(s, launch_fused, s, n_half, H, s->g.nk - H);
-            if (st != FDTD_OK) return st;
-            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
-            st = DISPATCH(s, launch_fused, s, n_half, 0, H);
-            if (st != FDTD_OK) return st;
-            st = DISPATCH(s, launch_fused, s, n_half, s->g.nk - H, s->g.nk);
-            if (st != FDTD_OK) return st;
+            if (src2) { s->src_t++; s->j_stale = true; }
+            *done = 2;
         } else {
-            st = exchange_fused(s, s->stream);
-            if (st != FDTD_OK) return st;
-            st = DISPATCH(s, launch_fused, s, n_half, 0, s->g.nk);
+            st = overlapped(s, s->ghosts_fused_valid,
+                            [&](int lo, int hi) { return DISPATCH(s, launch_fused, s, n_half, lo, hi); },
+                            [&](cudaStream_t q) { return exchange_fused(s, q); });
             if (st != FDTD_OK) return st;
         }
         s->cur ^= 1;
@@ -431,7 +565,7 @@ static fdtd_status_t advance_one(Solver* s) {
     }
     invalidate_ghosts(s);
     s->b_pending = true;
-    s->steps_done++;
+    s->steps_done += *done;
     return FDTD_OK;
 }
 
@@ -465,14 +599,14 @@ static void destroy_impl(Solver* s) {
 }
 
 static fdtd_status_t alloc_array(Solver* s, void** base, void** p) {
-    const size_t bytes = (size_t)s->g.plane * (size_t)(s->g.nk + 2) * s->esz;
+    const size_t bytes = (size_t)s->g.plane * (size_t)(s->g.nk + 2 * GHOST_PLANES) * s->esz;
     cudaError_t e = cudaMalloc(base, bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(FDTD_ERR_NOMEM, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
     }
     FDTD_CUDA_TRY(cudaMemsetAsync(*base, 0, bytes, s->stream));   // FDTD.cpp:21-32: all fields start at zero
-    *p = static_cast<char*>(*base) + (size_t)s->g.plane * s->esz;
+    *p = static_cast<char*>(*base) + (size_t)GHOST_PLANES * s->g.plane * s->esz;
     s->device_bytes += (int64_t)bytes;
     return FDTD_OK;
 }
@@ -546,6 +680,7 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
     // The fused pass serves the periodic solver with vector-aligned rows; everything else runs the two sweeps.
     const int V = (int)(16 / s->esz);
     s->fused = !s->has_pml && !(cfg->flags & FDTD_FLAG_NO_FUSION) && (P.Ni % V == 0);
+    s->t2 = s->fused && !(cfg->flags & FDTD_FLAG_NO_TEMPORAL) && s->g.nk >= 4;
 
     for (int c = 0; c < NCOMP && st == FDTD_OK; ++c) {
         st = alloc_array(s, &s->base[c][0], &s->p[c][0]);
@@ -718,11 +853,13 @@ fdtd_status_t fdtd_step(fdtd_solver_t* h, int nsteps) {
     fdtd_status_t st = check_handle(h, &s);
     if (st != FDTD_OK) return st;
     if (nsteps < 0) return fail(FDTD_ERR_BAD_ARGUMENT, "negative step count");
-    for (int t = 0; t < nsteps; ++t) {
-        st = advance_one(s);
+    for (int t = 0; t < nsteps;) {
+        int done = 1;
+        st = advance(s, nsteps - t, &done);
         if (st != FDTD_OK) return st;
+        t += done;
     }
-    return FDTD_OK;
+    return materialize_J(s);
 }
 
 fdtd_status_t fdtd_update_fields(fdtd_solver_t* h) { return fdtd_step(h, 1); }

@@ -1,10 +1,11 @@
 // fdtd_common.cuh -- shared device-side types and bit-exact arithmetic helpers.
 //
 // Storage layout (DESIGN.md "Data layout in HBM"): every field component is one SoA device
-// array of (nk + 2) planes x Nj rows x pitch elements; `pitch` is Ni rounded up to a multiple of
+// array of (nk + 2*GHOST_PLANES) planes x Nj rows x pitch elements; `pitch` is Ni rounded up to a multiple of
 // 128 bytes so that every row starts on a 128-byte line and 16-byte vector accesses never split.
-// The pointer held in Fields<T> addresses element (i=0, j=0, local plane 0); plane -1 and plane nk
-// are the k ghost planes used by the z-slab halo exchange.  Replaces the flat
+// The pointer held in Fields<T> addresses element (i=0, j=0, local plane 0); planes -2, -1 and nk, nk+1
+// are the k ghost planes used by the z-slab halo exchange (one per side for the one-step kernels, two for
+// the temporally blocked T2 pass).  Replaces the flat
 // std::vector / Kokkos::View of reference include/FDTD/shared.h:15, include/FDTD_kokkos/kokkos_shared.h:16.
 #pragma once
 
@@ -12,6 +13,8 @@
 #include <stdint.h>
 
 namespace fdtd_b200 {
+
+constexpr int GHOST_PLANES = 2;
 
 enum { EX = 0, EY, EZ, BX, BY, BZ, JX, JY, JZ, NCOMP };
 // split-field order inside Fields::SE / Fields::SB (reference include/FDTD/FDTD_PML.h:12-13)

@@ -1,0 +1,347 @@
+// fused_kernel_t2.cuh -- temporally blocked fused pass: TWO Yee steps per launch ("T2 pass").
+//
+// Replaces two consecutive calls of FDTD::update_fields() (reference src/FDTD/FDTD.cpp:153-157 =
+// update_B, update_E, update_B; Kokkos twin src/FDTD_kokkos/FDTD_kokkos.cpp:91-104) with ONE kernel:
+//
+//     stage A (step s)    B1 = round(round(B0 + h(E0)) [+ h(E0)])      n_half = 1 or 2, like fused_BE_kernel
+//                         E1 = E0 + g(B1, J_s)
+//     stage B (step s+1)  B2 = round(round(B1 + h(E1)) + h(E1))        trailing half of s merged with leading half of s+1
+//                         E2 = E1 + g(B2, J_{s+1})
+//
+// Every cell sees exactly the operations of the reference in the reference's order, so the result is
+// bit-identical to two single-step passes (tests/test_parity_gpu.py).  What changes is the HBM traffic:
+// read E0(3)+B0(3), write E2(3)+B2(3) = 12 words per cell per TWO steps = 6 words (48 B fp64) per
+// cell-step, against 12 for the one-step fused pass and 30 for the reference's three sweeps.
+//
+// Tile roles (V = cells per 16-byte vector; the dependency cone of one output cell reaches 2 cells down
+// and 2 cells up in i, j and k):
+//   * warp = 32 lanes x V cells of one row; lane 0 / lane 31 are the left / right halo lanes
+//     (2 halo cells fit in one lane for V = 2 and V = 4), lanes 1..30 store -> 30*V cells per row;
+//     i-neighbours travel by __shfl_up/down (north_star (b));
+//   * CTA = BY warps = BY consecutive rows; rows 0,1 and BY-2,BY-1 are halo rows, rows 2..BY-3 store;
+//     j-neighbours travel through four single-buffered shared-memory row exchanges (E0, B1, E1, B2),
+//     two __syncthreads per plane;
+//   * each thread streams a chunk of k planes upward; stage B runs one plane behind stage A.  Carried in
+//     registers: E0(k), B1(k-1), E1(k-1), B2(k-2).xy.  A chunk starts two planes early and ends one
+//     plane late (3 redundant plane iterations per chunk);
+//   * the six 16-byte vectors a thread needs per plane (E0(k+1) x3, B0(k) x3) arrive through a D-deep
+//     per-thread cp.async ring in shared memory (LDGSTS, L1 bypass), issued D-1 planes ahead: no register
+//     cost for the bytes in flight, and no barrier (each thread reads only what it copied itself);
+//   * periodic wrap: halo lanes / rows / planes read the wrapped address of the INPUT generation (E and B are
+//     double-buffered); on a z-slab rank the k halos are the two ghost planes on each side.
+//
+// J: stage A reads the J arrays (inside the host-tracked bounding box only).  Stage B reads the same arrays
+// (static J) unless a device-resident source is active, in which case the box of that source is evaluated in
+// the kernel for step s+1 -- ((amp*wx)*wy)*wz, the product order of perf-tests/sample/sample.cpp:26-31 --
+// i.e. source injection as a fused epilogue (north_star (c)).
+//
+// Requires Ni % V == 0 and nk >= 4 (the host falls back to the one-step pass otherwise).
+#pragma once
+
+#include "fused_kernel_v2.cuh"
+
+namespace fdtd_b200 {
+
+template <typename T>
+struct FusedT2Args {
+    Geom g;
+    Coefs c;
+    const T* Ein[3];
+    const T* Bin[3];
+    const T* J[3];
+    T* Eout[3];
+    T* Bout[3];
+    JBox jbox;
+    int k_lo, k_hi;   // local planes [k_lo, k_hi) produced by this launch
+    int kc;           // planes per CTA chunk
+    int n_half;       // stage A: 1 or 2 half steps of B (stage B always applies 2)
+    int j_quirk;      // Jx feeds all three components (FDTD_openmp semantics)
+    // device-resident source evaluated in-kernel for stage B
+    int src2;                  // 1: cells inside [s_lo, s_hi) take J = ((amp2*wx)*wy)*wz in stage B
+    int s_lo[3], s_hi[3];      // global box
+    const double* sw[3];       // device tables, indexed from s_lo
+    double amp2;
+};
+
+template <int BY, int D>
+constexpr size_t fused_t2_smem_bytes() {
+    return (size_t)(4 * 2 * BY * FUSED_BX + D * 6 * BY * FUSED_BX) * 16;
+}
+
+// B += n_half * h(E)   (FDTD.cpp:121-126).  e = E(k), ek = E(k+1), (ezu, exu) = Ez, Ex one row up,
+// (ez_nl, ey_nl) = Ez, Ey first element of the next lane.
+template <typename T, int V>
+__device__ __forceinline__ void t2_update_B(T (&b)[3][V], const T (&e)[3][V], const T (&ek)[3][V], const T (&ezu)[V],
+                                            const T (&exu)[V], const T ez_nl, const T ey_nl, const double cBx,
+                                            const double cBy, const double cBz, const bool two) {
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        const double ex = (double)e[0][q], ey = (double)e[1][q], ez = (double)e[2][q];
+        const double ezr = (double)((q == V - 1) ? ez_nl : e[2][(q + 1) % V]);
+        const double eyr = (double)((q == V - 1) ? ey_nl : e[1][(q + 1) % V]);
+        const double hx = dsub(dmul(cBz, dsub((double)ek[1][q], ey)), dmul(cBy, dsub((double)ezu[q], ez)));
+        const double hy = dsub(dmul(cBx, dsub(ezr, ez)), dmul(cBz, dsub((double)ek[0][q], ex)));
+        const double hz = dsub(dmul(cBy, dsub((double)exu[q], ex)), dmul(cBx, dsub(eyr, ey)));
+        T nbx = (T)dadd((double)b[0][q], hx);
+        T nby = (T)dadd((double)b[1][q], hy);
+        T nbz = (T)dadd((double)b[2][q], hz);
+        if (two) {
+            nbx = (T)dadd((double)nbx, hx);
+            nby = (T)dadd((double)nby, hy);
+            nbz = (T)dadd((double)nbz, hz);
+        }
+        b[0][q] = nbx; b[1][q] = nby; b[2][q] = nbz;
+    }
+}
+
+// E += g(B, J)   (FDTD.cpp:85-93 / kokkos_functors.h:81-89), in place.  b = B(k), (bxk, byk) = Bx, By at k-1,
+// (bzd, bxd) = Bz, Bx one row down, (bz_pl, by_pl) = Bz, By last element of the previous lane.
+template <typename T, int V>
+__device__ __forceinline__ void t2_update_E(T (&e)[3][V], const T (&b)[3][V], const T (&bxk)[V], const T (&byk)[V],
+                                            const T (&bzd)[V], const T (&bxd)[V], const T bz_pl, const T by_pl,
+                                            const double cEx, const double cEy, const double cEz, const double cJ,
+                                            const bool use_j, const T (&jv)[3][V]) {
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        const double bx = (double)b[0][q], by = (double)b[1][q], bz = (double)b[2][q];
+        const double bzl = (double)((q == 0) ? bz_pl : b[2][(q + V - 1) % V]);
+        const double byl = (double)((q == 0) ? by_pl : b[1][(q + V - 1) % V]);
+        double tx_ = dmul(cEy, dsub(bz, (double)bzd[q]));
+        double ty_ = dmul(cEz, dsub(bx, (double)bxk[q]));
+        double tz_ = dmul(cEx, dsub(by, byl));
+        if (use_j) {
+            tx_ = dadd(dmul(cJ, (double)jv[0][q]), tx_);
+            ty_ = dadd(dmul(cJ, (double)jv[1][q]), ty_);
+            tz_ = dadd(dmul(cJ, (double)jv[2][q]), tz_);
+        }
+        e[0][q] = (T)dadd((double)e[0][q], dsub(tx_, dmul(cEz, dsub(by, (double)byk[q]))));
+        e[1][q] = (T)dadd((double)e[1][q], dsub(ty_, dmul(cEx, dsub(bz, bzl))));
+        e[2][q] = (T)dadd((double)e[2][q], dsub(tz_, dmul(cEy, dsub(bx, (double)bxd[q]))));
+    }
+}
+
+template <typename T, int BY, int D, int MINB>
+__global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const FusedT2Args<T> a) {
+    constexpr int V = VecOf<T>::V;
+    constexpr int TJU = BY - 4;               // output rows per CTA
+    constexpr int TIU = FUSED_OUT_LANES * V;  // output cells per CTA row
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int ROWV = BY * FUSED_BX;       // vectors per exchange row set
+    using VT = typename FusedVec<T>::type;
+    static_assert(BY >= 5, "T2 pass needs at least one output row");
+    static_assert(D >= 2, "ring depth");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VT* const sE0 = reinterpret_cast<VT*>(smem_raw);   // [2 comps: z, x][BY][32]  old E(k) rows
+    VT* const sB1 = sE0 + 2 * ROWV;                    // B1(k) rows (z, x)
+    VT* const sE1 = sB1 + 2 * ROWV;                    // E1(k-1) rows (z, x)
+    VT* const sB2 = sE1 + 2 * ROWV;                    // B2(k-1) rows (z, x)
+    VT* const ring = sB2 + 2 * ROWV;                   // [D][6][BY][32]
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int Ni = a.g.Ni, Nj = a.g.Nj, nk = a.g.nk;
+    const int tid = ty * FUSED_BX + tx;
+    const int tyn = (ty + 1 < BY) ? ty + 1 : ty;   // row above (clamped: the top halo row's result is never used)
+    const int typ = (ty > 0) ? ty - 1 : ty;        // row below (clamped likewise)
+    const int xu = tyn * FUSED_BX + tx, xd = typ * FUSED_BX + tx;
+
+    // ---- roles ---------------------------------------------------------------------------------------------
+    const int i = blockIdx.x * TIU - V + tx * V;            // first cell of this lane (may be -V or >= Ni)
+    const bool lane_active = (i <= Ni);                     // i == Ni: right halo, wrapped to column 0
+    const int iw = (i < 0) ? i + Ni : ((i >= Ni) ? i - Ni : i);
+    const int j = blockIdx.y * TJU - 2 + ty;
+    const bool row_active = (j <= Nj + 1);
+    int jw = j % Nj;
+    if (jw < 0) jw += Nj;
+    const bool ld = lane_active && row_active;
+    const bool out = ld && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (i < Ni) && (ty >= 2) && (ty <= BY - 3) && (j < Nj);
+    const long long roff = (long long)jw * a.g.pitch + (lane_active ? iw : 0);
+
+    const int kb = a.k_lo + blockIdx.z * a.kc;
+    const int ke = min(kb + a.kc, a.k_hi);
+
+    const double cBx = a.c.cBx, cBy = a.c.cBy, cBz = a.c.cBz;
+    const double cEx = a.c.cEx, cEy = a.c.cEy, cEz = a.c.cEz, cJ = a.c.cJ;
+    const bool two_A = (a.n_half == 2);
+
+    // J may be non-zero only inside jbox (global coordinates).  Stage A needs it on every cell whose E1 feeds an
+    // output cell, halo lanes / rows included (their wrapped coordinates are tested); stage B only where it stores.
+    const bool j_ijA = !a.jbox.empty() && ld && (iw < a.jbox.hi[0]) && (iw + V > a.jbox.lo[0]) &&
+                       (jw >= a.jbox.lo[1]) && (jw < a.jbox.hi[1]);
+    const bool j_ijB = j_ijA && out;
+
+    // plane (element offset) holding local plane k of the input generation: index wrap on a single GPU,
+    // ghost planes -2, -1, nk, nk+1 on a slab rank
+    auto plane_of = [&](int k) -> long long {
+        if (a.g.wrap_k) {
+            if (k < 0) k += nk;
+            else if (k >= nk) k -= nk;
+        }
+        return (long long)k * a.g.plane;
+    };
+    // asynchronous copies for iteration k (old E(k+1), B0(k)) into ring slot `slot`
+    auto issue_ring = [&](int k, int slot) {
+        if (ld) {
+            const long long pe = plane_of(k + 1) + roff, pb = plane_of(k) + roff;
+            VT* s = ring + (size_t)slot * 6 * ROWV + tid;
+            cp_async16(s + 0 * ROWV, a.Ein[0] + pe);
+            cp_async16(s + 1 * ROWV, a.Ein[1] + pe);
+            cp_async16(s + 2 * ROWV, a.Ein[2] + pe);
+            cp_async16(s + 3 * ROWV, a.Bin[0] + pb);
+            cp_async16(s + 4 * ROWV, a.Bin[1] + pb);
+            cp_async16(s + 5 * ROWV, a.Bin[2] + pb);
+        }
+    };
+
+    // ---- carried state -------------------------------------------------------------------------------------
+    T e0[3][V];      // old E at plane k
+    T b1[3][V];      // B1 at plane k-1
+    T e1[3][V];      // E1 at plane k-1
+    T b2x[V], b2y[V];  // B2 (x, y) at plane k-2
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int q = 0; q < V; ++q) { e0[c][q] = (T)0; b1[c][q] = (T)0; e1[c][q] = (T)0; }
+#pragma unroll
+    for (int q = 0; q < V; ++q) { b2x[q] = (T)0; b2y[q] = (T)0; }
+
+    // ---- prologue: fill the ring, load old E(kb-2), publish its rows ------------------------------------------
+    const int k_first = kb - 2;
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d) {
+        if (k_first + d <= ke) issue_ring(k_first + d, d);
+        cp_async_commit();
+    }
+    if (ld) {
+        const long long p0 = plane_of(k_first) + roff;
+        ldg_vec<T, V>(a.Ein[0] + p0, e0[0]);
+        ldg_vec<T, V>(a.Ein[1] + p0, e0[1]);
+        ldg_vec<T, V>(a.Ein[2] + p0, e0[2]);
+    }
+    sE0[0 * ROWV + tid] = FusedVec<T>::pack(e0[2]);
+    sE0[1 * ROWV + tid] = FusedVec<T>::pack(e0[0]);
+    __syncthreads();
+
+    int slot = 0;
+#pragma unroll 1
+    for (int k = k_first; k <= ke; ++k) {
+        // ================= phase X: B1(k) =========================================================================
+        T en[3][V], b[3][V];
+        {
+            int nslot = slot + (D - 1);
+            if (nslot >= D) nslot -= D;
+            if (k + D - 1 <= ke) issue_ring(k + D - 1, nslot);
+            cp_async_commit();
+            cp_async_wait<D - 1>();
+            const VT* s = ring + (size_t)slot * 6 * ROWV + tid;
+            FusedVec<T>::unpack(s[0 * ROWV], en[0]);
+            FusedVec<T>::unpack(s[1 * ROWV], en[1]);
+            FusedVec<T>::unpack(s[2 * ROWV], en[2]);
+            FusedVec<T>::unpack(s[3 * ROWV], b[0]);
+            FusedVec<T>::unpack(s[4 * ROWV], b[1]);
+            FusedVec<T>::unpack(s[5 * ROWV], b[2]);
+            slot = (slot + 1 == D) ? 0 : slot + 1;
+        }
+        {
+            T ezu[V], exu[V];
+            FusedVec<T>::unpack(sE0[0 * ROWV + xu], ezu);
+            FusedVec<T>::unpack(sE0[1 * ROWV + xu], exu);
+            const T ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
+            const T ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
+            t2_update_B<T, V>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, two_A);
+        }
+        sB1[0 * ROWV + tid] = FusedVec<T>::pack(b[2]);
+        sB1[1 * ROWV + tid] = FusedVec<T>::pack(b[0]);
+        __syncthreads();   // barrier 1: B1(k) rows visible; everybody is done reading sE0 / sB2 of the previous plane
+
+        // ================= phase Y: E1(k), then B2(k-1) ==============================================================
+        sE0[0 * ROWV + tid] = FusedVec<T>::pack(en[2]);   // old E(k+1) rows for the next plane's phase X
+        sE0[1 * ROWV + tid] = FusedVec<T>::pack(en[0]);
+        const int kg = a.g.k0 + k;                           // global plane of stage A
+        {
+            T bzd[V], bxd[V], jv[3][V];
+            FusedVec<T>::unpack(sB1[0 * ROWV + xd], bzd);
+            FusedVec<T>::unpack(sB1[1 * ROWV + xd], bxd);
+            const T bz_pl = __shfl_up_sync(FULL, b[2][V - 1], 1);
+            const T by_pl = __shfl_up_sync(FULL, b[1][V - 1], 1);
+            // J of step s applies to E1(k) where k is an owned plane [0, nk) (halo planes recompute the
+            // neighbour's cells: same global coordinates, same J)
+            int kgw = kg;
+            if (kgw < 0) kgw += a.g.Nk; else if (kgw >= a.g.Nk) kgw -= a.g.Nk;
+            const bool use_j = j_ijA && (kgw >= a.jbox.lo[2]) && (kgw < a.jbox.hi[2]);
+            if (use_j) {
+                const long long pj = plane_of(k) + roff;
+                ldg_vec<T, V>(a.J[0] + pj, jv[0]);
+                ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
+                ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
+            }
+            // e0 (= old E(k)) becomes E1(k) in place
+            t2_update_E<T, V>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+        }
+        // now: e0 = E1(k), b = B1(k), b1 = B1(k-1), e1 = E1(k-1), en = old E(k+1)
+        {
+            T ezu[V], exu[V];
+            FusedVec<T>::unpack(sE1[0 * ROWV + xu], ezu);   // E1(k-1) one row up (written in phase Z of the previous plane)
+            FusedVec<T>::unpack(sE1[1 * ROWV + xu], exu);
+            const T ez_nl = __shfl_down_sync(FULL, e1[2][0], 1);
+            const T ey_nl = __shfl_down_sync(FULL, e1[1][0], 1);
+            // b1 (= B1(k-1)) becomes B2(k-1) in place
+            t2_update_B<T, V>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
+        }
+        sB2[0 * ROWV + tid] = FusedVec<T>::pack(b1[2]);
+        sB2[1 * ROWV + tid] = FusedVec<T>::pack(b1[0]);
+        __syncthreads();   // barrier 2: B2(k-1) rows and old E(k+1) rows visible; everybody is done reading sB1 / sE1
+
+        // ================= phase Z: E2(k-1), stores, carry =============================================================
+        sE1[0 * ROWV + tid] = FusedVec<T>::pack(e0[2]);   // E1(k) rows for the next plane's phase Y
+        sE1[1 * ROWV + tid] = FusedVec<T>::pack(e0[0]);
+        {
+            T bzd[V], bxd[V], jv[3][V];
+            FusedVec<T>::unpack(sB2[0 * ROWV + xd], bzd);
+            FusedVec<T>::unpack(sB2[1 * ROWV + xd], bxd);
+            const T bz_pl = __shfl_up_sync(FULL, b1[2][V - 1], 1);
+            const T by_pl = __shfl_up_sync(FULL, b1[1][V - 1], 1);
+            const int kB = k - 1;                          // plane of stage B (an owned plane whenever it is stored)
+            const int kgB = a.g.k0 + kB;
+            const bool use_j = j_ijB && (kgB >= a.jbox.lo[2]) && (kgB < a.jbox.hi[2]) && (kB >= kb) && (kB < ke);
+            if (use_j) {
+                const long long pj = (long long)kB * a.g.plane + roff;
+                ldg_vec<T, V>(a.J[0] + pj, jv[0]);
+                ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
+                ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
+                if (a.src2 && kgB >= a.s_lo[2] && kgB < a.s_hi[2] && jw >= a.s_lo[1] && jw < a.s_hi[1]) {
+                    const double wyz_y = a.sw[1][jw - a.s_lo[1]], wyz_z = a.sw[2][kgB - a.s_lo[2]];
+#pragma unroll
+                    for (int q = 0; q < V; ++q) {
+                        const int ii = i + q;
+                        if (ii >= a.s_lo[0] && ii < a.s_hi[0]) {
+                            const T v = (T)dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wyz_y), wyz_z);
+                            jv[0][q] = v; jv[1][q] = v; jv[2][q] = v;
+                        }
+                    }
+                }
+            }
+            // e1 (= E1(k-1)) becomes E2(k-1) in place
+            t2_update_E<T, V>(e1, b1, b2x, b2y, bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+            if (out && kB >= kb && kB < ke) {
+                const long long o = (long long)kB * a.g.plane + roff;
+                stg_vec<T, V>(a.Eout[0] + o, e1[0]);
+                stg_vec<T, V>(a.Eout[1] + o, e1[1]);
+                stg_vec<T, V>(a.Eout[2] + o, e1[2]);
+                stg_vec<T, V>(a.Bout[0] + o, b1[0]);
+                stg_vec<T, V>(a.Bout[1] + o, b1[1]);
+                stg_vec<T, V>(a.Bout[2] + o, b1[2]);
+            }
+        }
+        // carry: B2(k-1).xy, E1(k), B1(k), old E(k+1)
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            b2x[q] = b1[0][q]; b2y[q] = b1[1][q];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { e1[c][q] = e0[c][q]; b1[c][q] = b[c][q]; e0[c][q] = en[c][q]; }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace fdtd_b200

@@ -26,7 +26,7 @@ struct Solver {
     double* d_decay[3] = {nullptr, nullptr, nullptr};
     double* d_coef2[3] = {nullptr, nullptr, nullptr};
 
-    // Device arrays.  base[] are the cudaMalloc pointers ((nk+2) planes); p[] = base + one plane.
+    // Device arrays.  base[] are the cudaMalloc pointers ((nk + 2*GHOST_PLANES) planes); p[] = base + GHOST_PLANES planes.
     // E and B have two generations (ping-pong) when the fused pass is enabled; cur selects the live one.
     void* base[NCOMP][2] = {};
     void* p[NCOMP][2] = {};
@@ -34,6 +34,8 @@ struct Solver {
     void* split_p[2 * NSPLIT] = {};
     int cur = 0;
     bool fused = false;
+    bool t2 = false;               // fdtd_step(n >= 2) pairs steps into the temporally blocked T2 pass
+    bool j_stale = false;          // a T2 pass evaluated the device source in-kernel: the J arrays lag one step
     int64_t device_bytes = 0;
 
     cudaStream_t stream = nullptr;
@@ -47,6 +49,7 @@ struct Solver {
     bool ghosts_e_valid = false;   // top ghost planes of Ex, Ey hold the upper neighbour's current plane
     bool ghosts_b_valid = false;   // bottom ghost planes of Bx, By hold the lower neighbour's current plane
     bool ghosts_fused_valid = false;
+    bool ghosts_t2_valid = false;
 
     JBox jbox{};                   // where J may be non-zero
     // device-resident source (fdtd_set_source)

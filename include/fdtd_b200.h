@@ -75,6 +75,7 @@ typedef enum fdtd_status {
 #define FDTD_FLAG_NO_GRAPH 0x4u       /* never capture fdtd_step(n) into a CUDA graph */
 #define FDTD_FLAG_NO_OVERLAP 0x8u     /* multi-GPU: issue the halo exchange on the compute stream (no overlap) */
 #define FDTD_FLAG_NO_PML_SPLIT 0x10u  /* PML: one launch per sweep with a per-cell predicate instead of interior + shell launches */
+#define FDTD_FLAG_NO_TEMPORAL 0x20u   /* fdtd_step(n): never pair steps into the temporally blocked two-step pass */
 
 typedef enum fdtd_pml_mode {
     FDTD_PML_NONE = 0,     /* class FDTD: periodic everywhere */

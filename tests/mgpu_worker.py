@@ -56,6 +56,10 @@ def main():
                     if not np.array_equal(g.download(c), o.field(c)[kb:ke]):
                         failures += 1
                         print(f"[rank {rank}] MISMATCH mid-run {shape} pml={pml} fusion={fusion} comp {c}", flush=True)
+        # batched steps: fdtd_step(n) pairs steps into the temporally blocked T2 pass (two ghost planes per side,
+        # J ghost planes included) wherever the slab has >= 4 planes
+        o.step(steps + 1)
+        g.step(steps + 1)
         for c in range(6):
             if not np.array_equal(g.download(c), o.field(c)[kb:ke]):
                 failures += 1

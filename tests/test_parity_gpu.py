@@ -304,3 +304,72 @@ def test_large_grid_properties():
     g.step(3)
     for c in range(6):
         assert np.array_equal(g.download(c), np.full((n, n, n), float(c + 1)))
+
+
+# ---- temporally blocked two-step pass (fused_kernel_t2.cuh) ---------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,steps", [((16, 12, 10), 8), ((64, 64, 64), 5), ((32, 8, 4), 9), ((2, 1, 4), 6), ((4, 2, 5), 7),
+                                         ((60, 6, 5), 4), ((124, 20, 40), 6), ((8, 3, 70), 5), ((120, 9, 6), 2)])
+def test_temporal_blocking_bit_exact(shape, steps, dtype):
+    """fdtd_step(n) pairs steps into the T2 pass (two Yee steps per launch): must equal the oracle, and the
+    one-step fused pass, bit for bit -- distinct static Jx/Jy/Jz, tiles that do not divide the grid, wraps."""
+    Ni, Nj, Nk = shape
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), dtype=dtype)
+    _, g1 = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), dtype=dtype, temporal=False)
+    f = seeded_fields(31, (Nk, Nj, Ni), dtype=dtype, same_j=False)
+    load_both(o, g, f)
+    for c in range(9):
+        g1.upload(c, f[c])
+    l0, l1 = g.info().launches, g1.info().launches
+    o.step(steps); g.step(steps); g1.step(steps)
+    if g.info().fused:   # (rows that are not a multiple of the vector width run the two-sweep kernels)
+        assert g.info().launches - l0 == (steps + 1) // 2, "steps were not paired into T2 passes"
+        assert g1.info().launches - l1 == steps
+    assert_bit_equal(o, g, what=f"T2 {shape} {dtype}")
+    assert_bit_equal(o, g1, what=f"T1 {shape} {dtype}")
+    # a second batch starts from the pending-half-step state (n_half = 2 in stage A)
+    o.step(3); g.step(3)
+    assert_bit_equal(o, g, what=f"T2 second batch {shape}")
+
+
+@pytest.mark.parametrize("variant", range(10))
+def test_temporal_blocking_variants(variant, monkeypatch):
+    monkeypatch.setenv("FDTD_B200_T2_VARIANT", str(variant))
+    Ni, Nj, Nk = 68, 37, 21
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C))
+    load_both(o, g, seeded_fields(17, (Nk, Nj, Ni), same_j=False))
+    o.step(6); g.step(6)
+    assert_bit_equal(o, g, what=f"T2 variant {variant}")
+
+
+@pytest.mark.parametrize("active,steps", [(5, 12), (6, 12), (40, 100), (1, 4), (7, 7), (8, 7)])
+@pytest.mark.parametrize("n", [32])
+def test_temporal_blocking_device_source(n, active, steps):
+    """Device-resident source under the T2 pass: the second step of a pair is injected in the kernel, pairs never
+    straddle the step where the source retires, and the J arrays read back like the reference's."""
+    import math
+    PI, T, Tx = 3.14159265358, 8.0, 4.0 * C
+    lo, hi, _, _ = sample_source(n, steps)
+    amp = [math.sin(2.0 * PI * (float(t + 1) * 0.2) / T) for t in range(active)]
+    w = [[math.pow(math.cos(2.0 * PI * (float(i) * C) / Tx), 2.0) for i in range(lo[a], hi[a])] for a in range(3)]
+    o = Oracle(**sample_params(n))
+    g = fb.FDTD(params(n, n, n), 0.2)
+    rng = np.random.default_rng(5)
+    for c in range(6):
+        a = rng.uniform(-1, 1, size=(n, n, n))
+        o.field(c)[...] = a
+        g.upload(c, a)
+    g.set_source(lo, hi, w[0], w[1], w[2], amp)
+    for t in range(steps):
+        if t < active:
+            for k in range(lo[2], hi[2]):
+                for j in range(lo[1], hi[1]):
+                    for i in range(lo[0], hi[0]):
+                        v = ((amp[t] * w[0][i - lo[0]]) * w[1][j - lo[1]]) * w[2][k - lo[2]]
+                        for c in (6, 7, 8):
+                            o.field(c)[k, j, i] = v
+        elif t == active:
+            o.zeroed_currents()
+        o.update_fields()
+    g.step(steps)
+    assert_bit_equal(o, g, comps=range(9), what=f"T2 device source active={active} steps={steps}")

@@ -40,6 +40,8 @@ if __name__ == "__main__":
     ap.add_argument("--variants", type=int, nargs="+", default=[0, 1, 2, 3, 4, 5])
     ap.add_argument("--kc", type=int, nargs="+", default=[0])
     ap.add_argument("--pml", action="store_true")
+    ap.add_argument("--t2", type=int, nargs="*", default=[], help="T2 (two-step pass) variants to time")
+    ap.add_argument("--no-sweeps", action="store_true", help="skip the two-sweep and one-step rows")
     a = ap.parse_args()
     os.makedirs("gpurun_out", exist_ok=True)
     out = open("gpurun_out/sweep.jsonl", "a")
@@ -48,14 +50,23 @@ if __name__ == "__main__":
             dtype = np.float64 if dt == "f64" else np.float32
             W = 8 if dt == "f64" else 4
             rows = []
-            ms = time_config(n, dtype, False, a.steps)
-            rows.append(dict(n=n, dtype=dt, path="two-sweep", ms=ms))
-            for v in a.variants:
+            os.environ["FDTD_B200_NO_T2"] = "1"
+            if not a.no_sweeps:
+                ms = time_config(n, dtype, False, a.steps)
+                rows.append(dict(n=n, dtype=dt, path="two-sweep", ms=ms))
+            for v in ([] if a.no_sweeps else a.variants):
                 for kc in a.kc:
                     os.environ["FDTD_B200_FUSED_VARIANT"] = str(v)
                     os.environ["FDTD_B200_FUSED_KC"] = str(kc)
                     ms = time_config(n, dtype, True, a.steps)
                     rows.append(dict(n=n, dtype=dt, path=f"fused v{v} kc{kc}", ms=ms))
+            os.environ["FDTD_B200_NO_T2"] = "0"
+            for v in a.t2:
+                for kc in a.kc:
+                    os.environ["FDTD_B200_T2_VARIANT"] = str(v)
+                    os.environ["FDTD_B200_FUSED_KC"] = str(kc)
+                    ms = time_config(n, dtype, True, a.steps)
+                    rows.append(dict(n=n, dtype=dt, path=f"T2 v{v} kc{kc}", ms=ms))
             if a.pml:
                 ms = time_config(n, dtype, False, max(3, a.steps // 4), pml=0.0625)
                 rows.append(dict(n=n, dtype=dt, path="pml 0.0625 two-sweep", ms=ms))
