@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-fmad=false",                 # belt and braces: arithmetic already uses __dadd_rn/__dmul_rn (no contraction)
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
-]
+] + (["-DFDTD_T2_ABLATE"] if os.environ.get("FDTD_T2_ABLATE") else [])
 
 
 def nvcc() -> str:

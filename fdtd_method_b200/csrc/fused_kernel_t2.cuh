@@ -63,9 +63,38 @@ struct FusedT2Args {
     double amp2;
 };
 
+// ---- shared-memory plumbing ---------------------------------------------------------------------------------
+// Every shared access of a thread is [sa + compile-time offset] (one address register): exchange arrays are
+// (BY + 2) rows so that "one row up / down" is +-512 B with no clamping, the ring follows.
+constexpr int T2_ROWB = FUSED_BX * 16;   // bytes per exchange / ring row (32 lanes x 16 B)
+template <int BY> __host__ __device__ constexpr int t2_xq(int q) { return q * (BY + 2) * T2_ROWB; }          // exchange array q, own slot
+template <int BY> __host__ __device__ constexpr int t2_ring0() { return 8 * (BY + 2) * T2_ROWB - T2_ROWB; }   // ring slot 0 comp 0, rel. to sa
 template <int BY, int D>
 constexpr size_t fused_t2_smem_bytes() {
-    return (size_t)(4 * 2 * BY * FUSED_BX + D * 6 * BY * FUSED_BX) * 16;
+    return (size_t)(8 * (BY + 2) + D * 6 * BY) * T2_ROWB;
+}
+
+template <typename T> struct SmemIO;
+template <> struct SmemIO<double> {
+    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, double (&v)[2]) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v[0]), "=d"(v[1]) : "r"(a), "n"(OFF) : "memory");
+    }
+    template <int OFF> static __device__ __forceinline__ void st(unsigned a, const double (&v)[2]) {
+        asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v[0]), "d"(v[1]) : "memory");
+    }
+};
+template <> struct SmemIO<float> {
+    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, float (&v)[4]) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a), "n"(OFF) : "memory");
+    }
+    template <int OFF> static __device__ __forceinline__ void st(unsigned a, const float (&v)[4]) {
+        asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    }
+};
+template <int OFF>
+__device__ __forceinline__ void cp_async16_at(unsigned a, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0+%1], [%2], 16;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
 }
 
 // B += n_half * h(E)   (FDTD.cpp:121-126).  e = E(k), ek = E(k+1), (ezu, exu) = Ez, Ex one row up,
@@ -120,30 +149,27 @@ __device__ __forceinline__ void t2_update_E(T (&e)[3][V], const T (&b)[3][V], co
     }
 }
 
-template <typename T, int BY, int D, int MINB>
-__global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const FusedT2Args<T> a) {
+template <typename T, int BY, int D, bool TWO_A, bool HAS_J, int ABL>
+__device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     constexpr int V = VecOf<T>::V;
     constexpr int TJU = BY - 4;               // output rows per CTA
     constexpr int TIU = FUSED_OUT_LANES * V;  // output cells per CTA row
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int ROWV = BY * FUSED_BX;       // vectors per exchange row set
-    using VT = typename FusedVec<T>::type;
+    constexpr int UP = T2_ROWB, DN = -T2_ROWB;
+    constexpr int XE0z = t2_xq<BY>(0), XE0x = t2_xq<BY>(1), XB1z = t2_xq<BY>(2), XB1x = t2_xq<BY>(3);
+    constexpr int XE1z = t2_xq<BY>(4), XE1x = t2_xq<BY>(5), XB2z = t2_xq<BY>(6), XB2x = t2_xq<BY>(7);
+    constexpr int RING = t2_ring0<BY>();          // + slot * SLOTB + comp * COMPB
+    constexpr int COMPB = BY * T2_ROWB, SLOTB = 6 * COMPB;
+    using IO = SmemIO<T>;
     static_assert(BY >= 5, "T2 pass needs at least one output row");
     static_assert(D >= 2, "ring depth");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    VT* const sE0 = reinterpret_cast<VT*>(smem_raw);   // [2 comps: z, x][BY][32]  old E(k) rows
-    VT* const sB1 = sE0 + 2 * ROWV;                    // B1(k) rows (z, x)
-    VT* const sE1 = sB1 + 2 * ROWV;                    // E1(k-1) rows (z, x)
-    VT* const sB2 = sE1 + 2 * ROWV;                    // B2(k-1) rows (z, x)
-    VT* const ring = sB2 + 2 * ROWV;                   // [D][6][BY][32]
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int Ni = a.g.Ni, Nj = a.g.Nj, nk = a.g.nk;
-    const int tid = ty * FUSED_BX + tx;
-    const int tyn = (ty + 1 < BY) ? ty + 1 : ty;   // row above (clamped: the top halo row's result is never used)
-    const int typ = (ty > 0) ? ty - 1 : ty;        // row below (clamped likewise)
-    const int xu = tyn * FUSED_BX + tx, xd = typ * FUSED_BX + tx;
+    // the one shared-memory address register: own slot of exchange array 0
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)((ty + 1) * T2_ROWB + tx * 16);
 
     // ---- roles ---------------------------------------------------------------------------------------------
     const int i = blockIdx.x * TIU - V + tx * V;            // first cell of this lane (may be -V or >= Ni)
@@ -153,8 +179,14 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     const bool row_active = (j <= Nj + 1);
     int jw = j % Nj;
     if (jw < 0) jw += Nj;
-    const bool ld = lane_active && row_active;
-    const bool out = ld && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (i < Ni) && (ty >= 2) && (ty <= BY - 3) && (j < Nj);
+    // warp-uniform row roles: which stages this row has to produce for the CTA's output rows 2..BY-3
+    const bool needB1 = row_active && (ty <= BY - 2);
+    const bool needE1 = needB1 && (ty >= 1);
+    const bool needB2 = needE1 && (ty <= BY - 3);
+    const bool needE2 = needB2 && (ty >= 2) && (j < Nj);
+    const bool ldE = lane_active && row_active;
+    const bool ldB = lane_active && needB1;
+    const bool out = needE2 && lane_active && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (i < Ni);
     const long long roff = (long long)jw * a.g.pitch + (lane_active ? iw : 0);
 
     const int kb = a.k_lo + blockIdx.z * a.kc;
@@ -162,11 +194,10 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
 
     const double cBx = a.c.cBx, cBy = a.c.cBy, cBz = a.c.cBz;
     const double cEx = a.c.cEx, cEy = a.c.cEy, cEz = a.c.cEz, cJ = a.c.cJ;
-    const bool two_A = (a.n_half == 2);
 
     // J may be non-zero only inside jbox (global coordinates).  Stage A needs it on every cell whose E1 feeds an
     // output cell, halo lanes / rows included (their wrapped coordinates are tested); stage B only where it stores.
-    const bool j_ijA = !a.jbox.empty() && ld && (iw < a.jbox.hi[0]) && (iw + V > a.jbox.lo[0]) &&
+    const bool j_ijA = HAS_J && ldE && (iw < a.jbox.hi[0]) && (iw + V > a.jbox.lo[0]) &&
                        (jw >= a.jbox.lo[1]) && (jw < a.jbox.hi[1]);
     const bool j_ijB = j_ijA && out;
 
@@ -179,17 +210,19 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
         }
         return (long long)k * a.g.plane;
     };
-    // asynchronous copies for iteration k (old E(k+1), B0(k)) into ring slot `slot`
-    auto issue_ring = [&](int k, int slot) {
-        if (ld) {
-            const long long pe = plane_of(k + 1) + roff, pb = plane_of(k) + roff;
-            VT* s = ring + (size_t)slot * 6 * ROWV + tid;
-            cp_async16(s + 0 * ROWV, a.Ein[0] + pe);
-            cp_async16(s + 1 * ROWV, a.Ein[1] + pe);
-            cp_async16(s + 2 * ROWV, a.Ein[2] + pe);
-            cp_async16(s + 3 * ROWV, a.Bin[0] + pb);
-            cp_async16(s + 4 * ROWV, a.Bin[1] + pb);
-            cp_async16(s + 5 * ROWV, a.Bin[2] + pb);
+    // asynchronous copies for iteration k (old E(k+1), B0(k)) into the ring slot at shared address `sr`
+    auto issue_ring = [&](int k, unsigned sr) {
+        if (ldE) {
+            const long long pe = plane_of(k + 1) + roff;
+            cp_async16_at<RING + 0 * COMPB>(sr, a.Ein[0] + pe);
+            cp_async16_at<RING + 1 * COMPB>(sr, a.Ein[1] + pe);
+            cp_async16_at<RING + 2 * COMPB>(sr, a.Ein[2] + pe);
+        }
+        if (ldB) {
+            const long long pb = plane_of(k) + roff;
+            cp_async16_at<RING + 3 * COMPB>(sr, a.Bin[0] + pb);
+            cp_async16_at<RING + 4 * COMPB>(sr, a.Bin[1] + pb);
+            cp_async16_at<RING + 5 * COMPB>(sr, a.Bin[2] + pb);
         }
     };
 
@@ -209,17 +242,17 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     const int k_first = kb - 2;
 #pragma unroll
     for (int d = 0; d < D - 1; ++d) {
-        if (k_first + d <= ke) issue_ring(k_first + d, d);
+        if (k_first + d <= ke) issue_ring(k_first + d, sa + d * SLOTB);
         cp_async_commit();
     }
-    if (ld) {
+    if (ldE) {
         const long long p0 = plane_of(k_first) + roff;
         ldg_vec<T, V>(a.Ein[0] + p0, e0[0]);
         ldg_vec<T, V>(a.Ein[1] + p0, e0[1]);
         ldg_vec<T, V>(a.Ein[2] + p0, e0[2]);
     }
-    sE0[0 * ROWV + tid] = FusedVec<T>::pack(e0[2]);
-    sE0[1 * ROWV + tid] = FusedVec<T>::pack(e0[0]);
+    IO::template st<XE0z>(sa, e0[2]);
+    IO::template st<XE0x>(sa, e0[0]);
     __syncthreads();
 
     int slot = 0;
@@ -230,45 +263,46 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
         {
             int nslot = slot + (D - 1);
             if (nslot >= D) nslot -= D;
-            if (k + D - 1 <= ke) issue_ring(k + D - 1, nslot);
+            if (k + D - 1 <= ke && ABL != 3) issue_ring(k + D - 1, sa + nslot * SLOTB);
             cp_async_commit();
             cp_async_wait<D - 1>();
-            const VT* s = ring + (size_t)slot * 6 * ROWV + tid;
-            FusedVec<T>::unpack(s[0 * ROWV], en[0]);
-            FusedVec<T>::unpack(s[1 * ROWV], en[1]);
-            FusedVec<T>::unpack(s[2 * ROWV], en[2]);
-            FusedVec<T>::unpack(s[3 * ROWV], b[0]);
-            FusedVec<T>::unpack(s[4 * ROWV], b[1]);
-            FusedVec<T>::unpack(s[5 * ROWV], b[2]);
+            const unsigned sr = sa + slot * SLOTB;
+            IO::template ld<RING + 0 * COMPB>(sr, en[0]);
+            IO::template ld<RING + 1 * COMPB>(sr, en[1]);
+            IO::template ld<RING + 2 * COMPB>(sr, en[2]);
+            if (needB1) {
+                IO::template ld<RING + 3 * COMPB>(sr, b[0]);
+                IO::template ld<RING + 4 * COMPB>(sr, b[1]);
+                IO::template ld<RING + 5 * COMPB>(sr, b[2]);
+            }
             slot = (slot + 1 == D) ? 0 : slot + 1;
         }
-        {
+        if (needB1) {
             T ezu[V], exu[V];
-            FusedVec<T>::unpack(sE0[0 * ROWV + xu], ezu);
-            FusedVec<T>::unpack(sE0[1 * ROWV + xu], exu);
+            IO::template ld<XE0z + UP>(sa, ezu);
+            IO::template ld<XE0x + UP>(sa, exu);
             const T ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
             const T ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
-            t2_update_B<T, V>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, two_A);
+            if (ABL != 4) t2_update_B<T, V>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, TWO_A);
+            IO::template st<XB1z>(sa, b[2]);
+            IO::template st<XB1x>(sa, b[0]);
         }
-        sB1[0 * ROWV + tid] = FusedVec<T>::pack(b[2]);
-        sB1[1 * ROWV + tid] = FusedVec<T>::pack(b[0]);
-        __syncthreads();   // barrier 1: B1(k) rows visible; everybody is done reading sE0 / sB2 of the previous plane
+        if (ABL != 1) __syncthreads();   // barrier 1: B1(k) rows visible; everybody is done reading sE0 / sB2 of the previous plane
 
         // ================= phase Y: E1(k), then B2(k-1) ==============================================================
-        sE0[0 * ROWV + tid] = FusedVec<T>::pack(en[2]);   // old E(k+1) rows for the next plane's phase X
-        sE0[1 * ROWV + tid] = FusedVec<T>::pack(en[0]);
-        const int kg = a.g.k0 + k;                           // global plane of stage A
-        {
+        IO::template st<XE0z>(sa, en[2]);   // old E(k+1) rows for the next plane's phase X
+        IO::template st<XE0x>(sa, en[0]);
+        if (needE1) {
             T bzd[V], bxd[V], jv[3][V];
-            FusedVec<T>::unpack(sB1[0 * ROWV + xd], bzd);
-            FusedVec<T>::unpack(sB1[1 * ROWV + xd], bxd);
+            IO::template ld<XB1z + DN>(sa, bzd);
+            IO::template ld<XB1x + DN>(sa, bxd);
             const T bz_pl = __shfl_up_sync(FULL, b[2][V - 1], 1);
             const T by_pl = __shfl_up_sync(FULL, b[1][V - 1], 1);
-            // J of step s applies to E1(k) where k is an owned plane [0, nk) (halo planes recompute the
-            // neighbour's cells: same global coordinates, same J)
-            int kgw = kg;
+            // J of step s applies to E1(k) on owned planes and on the halo planes that recompute a neighbour's
+            // cells (same global coordinates, same J)
+            int kgw = a.g.k0 + k;
             if (kgw < 0) kgw += a.g.Nk; else if (kgw >= a.g.Nk) kgw -= a.g.Nk;
-            const bool use_j = j_ijA && (kgw >= a.jbox.lo[2]) && (kgw < a.jbox.hi[2]);
+            const bool use_j = HAS_J && j_ijA && (kgw >= a.jbox.lo[2]) && (kgw < a.jbox.hi[2]);
             if (use_j) {
                 const long long pj = plane_of(k) + roff;
                 ldg_vec<T, V>(a.J[0] + pj, jv[0]);
@@ -276,54 +310,57 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
                 ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
             }
             // e0 (= old E(k)) becomes E1(k) in place
-            t2_update_E<T, V>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+            if (ABL != 4) t2_update_E<T, V>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
         }
         // now: e0 = E1(k), b = B1(k), b1 = B1(k-1), e1 = E1(k-1), en = old E(k+1)
-        {
+        if (needB2) {
             T ezu[V], exu[V];
-            FusedVec<T>::unpack(sE1[0 * ROWV + xu], ezu);   // E1(k-1) one row up (written in phase Z of the previous plane)
-            FusedVec<T>::unpack(sE1[1 * ROWV + xu], exu);
+            IO::template ld<XE1z + UP>(sa, ezu);   // E1(k-1) one row up (written in phase Z of the previous plane)
+            IO::template ld<XE1x + UP>(sa, exu);
             const T ez_nl = __shfl_down_sync(FULL, e1[2][0], 1);
             const T ey_nl = __shfl_down_sync(FULL, e1[1][0], 1);
             // b1 (= B1(k-1)) becomes B2(k-1) in place
-            t2_update_B<T, V>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
+            if (ABL != 4) t2_update_B<T, V>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
+            IO::template st<XB2z>(sa, b1[2]);
+            IO::template st<XB2x>(sa, b1[0]);
         }
-        sB2[0 * ROWV + tid] = FusedVec<T>::pack(b1[2]);
-        sB2[1 * ROWV + tid] = FusedVec<T>::pack(b1[0]);
-        __syncthreads();   // barrier 2: B2(k-1) rows and old E(k+1) rows visible; everybody is done reading sB1 / sE1
+        if (ABL != 1) __syncthreads();   // barrier 2: B2(k-1) rows and old E(k+1) rows visible; everybody is done reading sB1 / sE1
 
         // ================= phase Z: E2(k-1), stores, carry =============================================================
-        sE1[0 * ROWV + tid] = FusedVec<T>::pack(e0[2]);   // E1(k) rows for the next plane's phase Y
-        sE1[1 * ROWV + tid] = FusedVec<T>::pack(e0[0]);
-        {
+        if (needE1) {
+            IO::template st<XE1z>(sa, e0[2]);   // E1(k) rows for the next plane's phase Y
+            IO::template st<XE1x>(sa, e0[0]);
+        }
+        if (needE2) {
             T bzd[V], bxd[V], jv[3][V];
-            FusedVec<T>::unpack(sB2[0 * ROWV + xd], bzd);
-            FusedVec<T>::unpack(sB2[1 * ROWV + xd], bxd);
+            IO::template ld<XB2z + DN>(sa, bzd);
+            IO::template ld<XB2x + DN>(sa, bxd);
             const T bz_pl = __shfl_up_sync(FULL, b1[2][V - 1], 1);
             const T by_pl = __shfl_up_sync(FULL, b1[1][V - 1], 1);
             const int kB = k - 1;                          // plane of stage B (an owned plane whenever it is stored)
             const int kgB = a.g.k0 + kB;
-            const bool use_j = j_ijB && (kgB >= a.jbox.lo[2]) && (kgB < a.jbox.hi[2]) && (kB >= kb) && (kB < ke);
+            const bool stored = (kB >= kb) && (kB < ke);
+            const bool use_j = HAS_J && j_ijB && stored && (kgB >= a.jbox.lo[2]) && (kgB < a.jbox.hi[2]);
             if (use_j) {
                 const long long pj = (long long)kB * a.g.plane + roff;
                 ldg_vec<T, V>(a.J[0] + pj, jv[0]);
                 ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
                 ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
                 if (a.src2 && kgB >= a.s_lo[2] && kgB < a.s_hi[2] && jw >= a.s_lo[1] && jw < a.s_hi[1]) {
-                    const double wyz_y = a.sw[1][jw - a.s_lo[1]], wyz_z = a.sw[2][kgB - a.s_lo[2]];
+                    const double wy = a.sw[1][jw - a.s_lo[1]], wz = a.sw[2][kgB - a.s_lo[2]];
 #pragma unroll
                     for (int q = 0; q < V; ++q) {
                         const int ii = i + q;
                         if (ii >= a.s_lo[0] && ii < a.s_hi[0]) {
-                            const T v = (T)dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wyz_y), wyz_z);
+                            const T v = (T)dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wy), wz);
                             jv[0][q] = v; jv[1][q] = v; jv[2][q] = v;
                         }
                     }
                 }
             }
             // e1 (= E1(k-1)) becomes E2(k-1) in place
-            t2_update_E<T, V>(e1, b1, b2x, b2y, bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
-            if (out && kB >= kb && kB < ke) {
+            if (ABL != 4) t2_update_E<T, V>(e1, b1, b2x, b2y, bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+            if (out && stored && ABL != 2) {
                 const long long o = (long long)kB * a.g.plane + roff;
                 stg_vec<T, V>(a.Eout[0] + o, e1[0]);
                 stg_vec<T, V>(a.Eout[1] + o, e1[1]);
@@ -342,6 +379,27 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
         }
     }
     cp_async_wait<0>();
+}
+
+// Does the footprint [lo, hi) of a tile (unwrapped coordinates, may stick out of [0, N) by the halo) meet the
+// box [blo, bhi) or one of its periodic images?
+__device__ __forceinline__ bool t2_meets(int lo, int hi, int blo, int bhi, int N) {
+    return (lo < bhi && hi > blo) || (lo < bhi - N && hi > blo - N) || (lo < bhi + N && hi > blo + N);
+}
+
+template <typename T, int BY, int D, int MINB, bool TWO_A, int ABL = 0>
+__global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const FusedT2Args<T> a) {
+    constexpr int V = VecOf<T>::V;
+    // CTA-uniform: only the few tiles whose footprint (halo included) meets the box where J may be non-zero run
+    // the loop that knows about currents; everybody else runs the lean one.
+    const int i0 = blockIdx.x * (FUSED_OUT_LANES * V) - V, j0 = blockIdx.y * (BY - 4) - 2;
+    const int kb = a.k_lo + blockIdx.z * a.kc;
+    const int k0 = a.g.k0 + kb - 2, k1 = a.g.k0 + min(kb + a.kc, a.k_hi) + 1;
+    const bool has_j = !a.jbox.empty() && t2_meets(i0, i0 + FUSED_BX * V, a.jbox.lo[0], a.jbox.hi[0], a.g.Ni) &&
+                       t2_meets(j0, j0 + BY, a.jbox.lo[1], a.jbox.hi[1], a.g.Nj) &&
+                       t2_meets(k0, k1, a.jbox.lo[2], a.jbox.hi[2], a.g.Nk);
+    if (has_j) fused_BE_T2_body<T, BY, D, TWO_A, true, ABL>(a);
+    else fused_BE_T2_body<T, BY, D, TWO_A, false, ABL>(a);
 }
 
 }  // namespace fdtd_b200
