@@ -250,22 +250,22 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
 }
 
 // ---- temporally blocked pass: two Yee steps per launch (fused_kernel_t2.cuh) -------------------------------
-// Variant table <BY rows per CTA, ring depth D, min CTAs/SM>; FDTD_B200_T2_VARIANT picks one.
+// Variant table <BY rows per CTA, min CTAs/SM>; FDTD_B200_T2_VARIANT picks one.
 static int t2_variant() {
     const char* e = std::getenv("FDTD_B200_T2_VARIANT");
     return e ? std::atoi(e) : -1;
 }
 
-template <typename T, int BY, int D, int MINB, int ABL = 0>
+template <typename T, int BY, int MINB, int ABL = 0>
 static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
     constexpr int V = VecOf<T>::V;
     constexpr int TIU = FUSED_OUT_LANES * V;
     constexpr int TJU = BY - 4;
-    constexpr size_t smem = fused_t2_smem_bytes<BY, D>();
+    constexpr size_t smem = fused_t2_smem_bytes<BY>();
     static bool configured[16] = {};
     if (!configured[s->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, D, MINB, true, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, D, MINB, false, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, MINB, true, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, MINB, false, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[s->device & 15] = true;
     }
@@ -281,8 +281,8 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
     if (kc > np) kc = np;
     a.kc = kc;
     const int gz = (np + kc - 1) / kc;
-    if (a.n_half == 2) fused_BE_T2_kernel<T, BY, D, MINB, true, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
-    else fused_BE_T2_kernel<T, BY, D, MINB, false, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
+    if (a.n_half == 2) fused_BE_T2_kernel<T, BY, MINB, true, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
+    else fused_BE_T2_kernel<T, BY, MINB, false, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -306,20 +306,16 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int sr
     if (variant < 0) variant = 0;
     switch (variant) {
         default:
-        case 0: e = launch_t2_variant<T, 8, 3, 2>(s, a); break;
-        case 1: e = launch_t2_variant<T, 8, 2, 2>(s, a); break;
-        case 2: e = launch_t2_variant<T, 12, 3, 1>(s, a); break;
-        case 3: e = launch_t2_variant<T, 16, 3, 1>(s, a); break;
-        case 4: e = launch_t2_variant<T, 16, 2, 1>(s, a); break;
-        case 5: e = launch_t2_variant<T, 10, 2, 2>(s, a); break;
-        case 6: e = launch_t2_variant<T, 14, 3, 1>(s, a); break;
-        case 7: e = launch_t2_variant<T, 14, 2, 1>(s, a); break;
-        case 8: e = launch_t2_variant<T, 12, 2, 1>(s, a); break;
+        case 0: e = launch_t2_variant<T, 16, 1>(s, a); break;
+        case 1: e = launch_t2_variant<T, 8, 2>(s, a); break;
+        case 2: e = launch_t2_variant<T, 12, 1>(s, a); break;
+        case 3: e = launch_t2_variant<T, 14, 1>(s, a); break;
+        case 4: e = launch_t2_variant<T, 10, 2>(s, a); break;
 #ifdef FDTD_T2_ABLATE   /* timing experiments only: results are wrong */
-        case 11: e = launch_t2_variant<T, 16, 3, 1, 1>(s, a); break;
-        case 12: e = launch_t2_variant<T, 16, 3, 1, 2>(s, a); break;
-        case 13: e = launch_t2_variant<T, 16, 3, 1, 3>(s, a); break;
-        case 14: e = launch_t2_variant<T, 16, 3, 1, 4>(s, a); break;
+        case 11: e = launch_t2_variant<T, 16, 1, 1>(s, a); break;
+        case 12: e = launch_t2_variant<T, 16, 1, 2>(s, a); break;
+        case 13: e = launch_t2_variant<T, 16, 1, 3>(s, a); break;
+        case 14: e = launch_t2_variant<T, 16, 1, 4>(s, a); break;
 #endif
     }
     if (e != cudaSuccess) return cuda_fail(e, "fused_BE_T2_kernel launch");

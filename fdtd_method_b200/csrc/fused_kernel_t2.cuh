@@ -24,9 +24,12 @@
 //   * each thread streams a chunk of k planes upward; stage B runs one plane behind stage A.  Carried in
 //     registers: E0(k), B1(k-1), E1(k-1), B2(k-2).xy.  A chunk starts two planes early and ends one
 //     plane late (3 redundant plane iterations per chunk);
-//   * the six 16-byte vectors a thread needs per plane (E0(k+1) x3, B0(k) x3) arrive through a D-deep
-//     per-thread cp.async ring in shared memory (LDGSTS, L1 bypass), issued D-1 planes ahead: no register
-//     cost for the bytes in flight, and no barrier (each thread reads only what it copied itself);
+//   * the k loop is unrolled three times with the register sets rotating (E0(k+1) -> E0/E1(k) -> E1/E2(k-1),
+//     B0/B1(k) -> B1/B2(k-1) -> B2(k-2)), so nothing is copied between planes;
+//   * the six 16-byte vectors a thread needs per plane (E0(k+1) x3, B0(k) x3) arrive through a 3-slot
+//     per-thread cp.async ring in shared memory (LDGSTS, L1 bypass), issued two planes ahead: no register
+//     cost for the bytes in flight, and no barrier (each thread reads only what it copied itself).  (Bulk / TMA
+//     row copies were measured and lost: 512-byte copies are too small, see DESIGN.md.)
 //   * periodic wrap: halo lanes / rows / planes read the wrapped address of the INPUT generation (E and B are
 //     double-buffered); on a z-slab rank the k halos are the two ghost planes on each side.
 //
@@ -69,9 +72,10 @@ struct FusedT2Args {
 constexpr int T2_ROWB = FUSED_BX * 16;   // bytes per exchange / ring row (32 lanes x 16 B)
 template <int BY> __host__ __device__ constexpr int t2_xq(int q) { return q * (BY + 2) * T2_ROWB; }          // exchange array q, own slot
 template <int BY> __host__ __device__ constexpr int t2_ring0() { return 8 * (BY + 2) * T2_ROWB - T2_ROWB; }   // ring slot 0 comp 0, rel. to sa
-template <int BY, int D>
+constexpr int T2_D = 3;                  // ring depth = unroll factor of the k loop
+template <int BY>
 constexpr size_t fused_t2_smem_bytes() {
-    return (size_t)(8 * (BY + 2) + D * 6 * BY) * T2_ROWB;
+    return (size_t)(8 * (BY + 2) + T2_D * 6 * BY) * T2_ROWB;
 }
 
 template <typename T> struct SmemIO;
@@ -92,11 +96,6 @@ template <> struct SmemIO<float> {
         asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
     }
 };
-template <int OFF>
-__device__ __forceinline__ void cp_async16_at(unsigned a, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0+%1], [%2], 16;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
-}
-
 // B += n_half * h(E)   (FDTD.cpp:121-126).  e = E(k), ek = E(k+1), (ezu, exu) = Ez, Ex one row up,
 // (ez_nl, ey_nl) = Ez, Ey first element of the next lane.
 template <typename T, int V>
@@ -149,208 +148,161 @@ __device__ __forceinline__ void t2_update_E(T (&e)[3][V], const T (&b)[3][V], co
     }
 }
 
-template <typename T, int BY, int D, bool TWO_A, bool HAS_J, int ABL>
-__device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
+// Per-thread constants of the pass (everything the plane iteration needs besides the register sets).
+template <typename T>
+struct T2Ctx {
+    unsigned sa;            // shared address of the thread's slot in exchange array 0
+    int i, jw;
+    int kb, ke;
+    bool needB1, needE1, needB2, needE2, ldE, out, j_ijA, j_ijB;
+    long long roff;         // element offset of (jw, iw) inside a plane
+};
+
+template <typename T>
+__device__ __forceinline__ long long t2_plane_of(const FusedT2Args<T>& a, int k) {
+    // plane (element offset) holding local plane k of the input generation: index wrap on a single GPU,
+    // ghost planes -2, -1, nk, nk+1 on a slab rank
+    if (a.g.wrap_k) {
+        if (k < 0) k += a.g.nk;
+        else if (k >= a.g.nk) k -= a.g.nk;
+    }
+    return (long long)k * a.g.plane;
+}
+
+template <int OFF>
+__device__ __forceinline__ void cp_async16_at(unsigned a, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0+%1], [%2], 16;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
+}
+
+// Asynchronous copies (LDGSTS, L1 bypass) of plane iteration kk into ring slot SLOT: old E(kk+1) and, for the rows
+// that produce B1, B0(kk).  Every thread copies the six vectors it will read back itself, so the ring needs no
+// barrier, only cp.async.wait_group.
+template <typename T, int BY, int SLOT>
+__device__ __forceinline__ void t2_issue_slot(const FusedT2Args<T>& a, const T2Ctx<T>& c, const int kk) {
+    constexpr int COMPB = BY * T2_ROWB, SLOTB = 6 * COMPB;
+    constexpr int RING = t2_ring0<BY>() + SLOT * SLOTB;
+    if (c.ldE) {
+        const long long pe = t2_plane_of(a, kk + 1) + c.roff;
+        cp_async16_at<RING + 0 * COMPB>(c.sa, a.Ein[0] + pe);
+        cp_async16_at<RING + 1 * COMPB>(c.sa, a.Ein[1] + pe);
+        cp_async16_at<RING + 2 * COMPB>(c.sa, a.Ein[2] + pe);
+        if (c.needB1) {
+            const long long pb = t2_plane_of(a, kk) + c.roff;
+            cp_async16_at<RING + 3 * COMPB>(c.sa, a.Bin[0] + pb);
+            cp_async16_at<RING + 4 * COMPB>(c.sa, a.Bin[1] + pb);
+            cp_async16_at<RING + 5 * COMPB>(c.sa, a.Bin[2] + pb);
+        }
+    }
+}
+
+// One plane iteration.  Register sets by role on entry:
+//   en : free -> old E(k+1)           e0 : old E(k) -> E1(k)          e1 : E1(k-1) -> E2(k-1) (stored)
+//   b  : free -> B0(k) -> B1(k)        b1 : B1(k-1) -> B2(k-1) (stored)  b2 : B2(k-2) (x, y used)
+template <typename T, int BY, bool TWO_A, bool HAS_J, int ABL, int SLOT>
+__device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>& c, const int k,
+                                         T (&en)[3][VecOf<T>::V], T (&e0)[3][VecOf<T>::V], T (&e1)[3][VecOf<T>::V],
+                                         T (&b)[3][VecOf<T>::V], T (&b1)[3][VecOf<T>::V], T (&b2)[3][VecOf<T>::V]) {
     constexpr int V = VecOf<T>::V;
-    constexpr int TJU = BY - 4;               // output rows per CTA
-    constexpr int TIU = FUSED_OUT_LANES * V;  // output cells per CTA row
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int UP = T2_ROWB, DN = -T2_ROWB;
     constexpr int XE0z = t2_xq<BY>(0), XE0x = t2_xq<BY>(1), XB1z = t2_xq<BY>(2), XB1x = t2_xq<BY>(3);
     constexpr int XE1z = t2_xq<BY>(4), XE1x = t2_xq<BY>(5), XB2z = t2_xq<BY>(6), XB2x = t2_xq<BY>(7);
-    constexpr int RING = t2_ring0<BY>();          // + slot * SLOTB + comp * COMPB
     constexpr int COMPB = BY * T2_ROWB, SLOTB = 6 * COMPB;
+    constexpr int RING = t2_ring0<BY>() + SLOT * SLOTB;
+    constexpr int NEXT = (SLOT + T2_D - 1) % T2_D;     // slot freed by the previous plane
     using IO = SmemIO<T>;
-    static_assert(BY >= 5, "T2 pass needs at least one output row");
-    static_assert(D >= 2, "ring depth");
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int Ni = a.g.Ni, Nj = a.g.Nj, nk = a.g.nk;
-    // the one shared-memory address register: own slot of exchange array 0
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)((ty + 1) * T2_ROWB + tx * 16);
-
-    // ---- roles ---------------------------------------------------------------------------------------------
-    const int i = blockIdx.x * TIU - V + tx * V;            // first cell of this lane (may be -V or >= Ni)
-    const bool lane_active = (i <= Ni);                     // i == Ni: right halo, wrapped to column 0
-    const int iw = (i < 0) ? i + Ni : ((i >= Ni) ? i - Ni : i);
-    const int j = blockIdx.y * TJU - 2 + ty;
-    const bool row_active = (j <= Nj + 1);
-    int jw = j % Nj;
-    if (jw < 0) jw += Nj;
-    // warp-uniform row roles: which stages this row has to produce for the CTA's output rows 2..BY-3
-    const bool needB1 = row_active && (ty <= BY - 2);
-    const bool needE1 = needB1 && (ty >= 1);
-    const bool needB2 = needE1 && (ty <= BY - 3);
-    const bool needE2 = needB2 && (ty >= 2) && (j < Nj);
-    const bool ldE = lane_active && row_active;
-    const bool ldB = lane_active && needB1;
-    const bool out = needE2 && lane_active && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (i < Ni);
-    const long long roff = (long long)jw * a.g.pitch + (lane_active ? iw : 0);
-
-    const int kb = a.k_lo + blockIdx.z * a.kc;
-    const int ke = min(kb + a.kc, a.k_hi);
-
+    const unsigned sa = c.sa;
     const double cBx = a.c.cBx, cBy = a.c.cBy, cBz = a.c.cBz;
     const double cEx = a.c.cEx, cEy = a.c.cEy, cEz = a.c.cEz, cJ = a.c.cJ;
 
-    // J may be non-zero only inside jbox (global coordinates).  Stage A needs it on every cell whose E1 feeds an
-    // output cell, halo lanes / rows included (their wrapped coordinates are tested); stage B only where it stores.
-    const bool j_ijA = HAS_J && ldE && (iw < a.jbox.hi[0]) && (iw + V > a.jbox.lo[0]) &&
-                       (jw >= a.jbox.lo[1]) && (jw < a.jbox.hi[1]);
-    const bool j_ijB = j_ijA && out;
-
-    // plane (element offset) holding local plane k of the input generation: index wrap on a single GPU,
-    // ghost planes -2, -1, nk, nk+1 on a slab rank
-    auto plane_of = [&](int k) -> long long {
-        if (a.g.wrap_k) {
-            if (k < 0) k += nk;
-            else if (k >= nk) k -= nk;
-        }
-        return (long long)k * a.g.plane;
-    };
-    // asynchronous copies for iteration k (old E(k+1), B0(k)) into the ring slot at shared address `sr`
-    auto issue_ring = [&](int k, unsigned sr) {
-        if (ldE) {
-            const long long pe = plane_of(k + 1) + roff;
-            cp_async16_at<RING + 0 * COMPB>(sr, a.Ein[0] + pe);
-            cp_async16_at<RING + 1 * COMPB>(sr, a.Ein[1] + pe);
-            cp_async16_at<RING + 2 * COMPB>(sr, a.Ein[2] + pe);
-        }
-        if (ldB) {
-            const long long pb = plane_of(k) + roff;
-            cp_async16_at<RING + 3 * COMPB>(sr, a.Bin[0] + pb);
-            cp_async16_at<RING + 4 * COMPB>(sr, a.Bin[1] + pb);
-            cp_async16_at<RING + 5 * COMPB>(sr, a.Bin[2] + pb);
-        }
-    };
-
-    // ---- carried state -------------------------------------------------------------------------------------
-    T e0[3][V];      // old E at plane k
-    T b1[3][V];      // B1 at plane k-1
-    T e1[3][V];      // E1 at plane k-1
-    T b2x[V], b2y[V];  // B2 (x, y) at plane k-2
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int q = 0; q < V; ++q) { e0[c][q] = (T)0; b1[c][q] = (T)0; e1[c][q] = (T)0; }
-#pragma unroll
-    for (int q = 0; q < V; ++q) { b2x[q] = (T)0; b2y[q] = (T)0; }
-
-    // ---- prologue: fill the ring, load old E(kb-2), publish its rows ------------------------------------------
-    const int k_first = kb - 2;
-#pragma unroll
-    for (int d = 0; d < D - 1; ++d) {
-        if (k_first + d <= ke) issue_ring(k_first + d, sa + d * SLOTB);
-        cp_async_commit();
+    // ================= phase X: B1(k) =============================================================================
+    if (k + T2_D - 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, NEXT>(a, c, k + T2_D - 1);
+    cp_async_commit();
+    cp_async_wait<T2_D - 1>();
+    IO::template ld<RING + 1 * COMPB>(sa, en[1]);
+    IO::template ld<RING + 0 * COMPB>(sa, en[0]);
+    IO::template ld<RING + 2 * COMPB>(sa, en[2]);
+    if (c.needB1) {
+        IO::template ld<RING + 3 * COMPB>(sa, b[0]);
+        IO::template ld<RING + 4 * COMPB>(sa, b[1]);
+        IO::template ld<RING + 5 * COMPB>(sa, b[2]);
+        T ezu[V], exu[V];
+        IO::template ld<XE0z + UP>(sa, ezu);
+        IO::template ld<XE0x + UP>(sa, exu);
+        const T ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
+        const T ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
+        if (ABL != 4) t2_update_B<T, V>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, TWO_A);
+        IO::template st<XB1z>(sa, b[2]);
+        IO::template st<XB1x>(sa, b[0]);
     }
-    if (ldE) {
-        const long long p0 = plane_of(k_first) + roff;
-        ldg_vec<T, V>(a.Ein[0] + p0, e0[0]);
-        ldg_vec<T, V>(a.Ein[1] + p0, e0[1]);
-        ldg_vec<T, V>(a.Ein[2] + p0, e0[2]);
-    }
-    IO::template st<XE0z>(sa, e0[2]);
-    IO::template st<XE0x>(sa, e0[0]);
-    __syncthreads();
+    if (ABL != 1) __syncthreads();   // barrier 1: B1(k) rows visible; everybody is done reading sE0 / sB2 of the previous plane
 
-    int slot = 0;
-#pragma unroll 1
-    for (int k = k_first; k <= ke; ++k) {
-        // ================= phase X: B1(k) =========================================================================
-        T en[3][V], b[3][V];
-        {
-            int nslot = slot + (D - 1);
-            if (nslot >= D) nslot -= D;
-            if (k + D - 1 <= ke && ABL != 3) issue_ring(k + D - 1, sa + nslot * SLOTB);
-            cp_async_commit();
-            cp_async_wait<D - 1>();
-            const unsigned sr = sa + slot * SLOTB;
-            IO::template ld<RING + 0 * COMPB>(sr, en[0]);
-            IO::template ld<RING + 1 * COMPB>(sr, en[1]);
-            IO::template ld<RING + 2 * COMPB>(sr, en[2]);
-            if (needB1) {
-                IO::template ld<RING + 3 * COMPB>(sr, b[0]);
-                IO::template ld<RING + 4 * COMPB>(sr, b[1]);
-                IO::template ld<RING + 5 * COMPB>(sr, b[2]);
-            }
-            slot = (slot + 1 == D) ? 0 : slot + 1;
-        }
-        if (needB1) {
-            T ezu[V], exu[V];
-            IO::template ld<XE0z + UP>(sa, ezu);
-            IO::template ld<XE0x + UP>(sa, exu);
-            const T ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
-            const T ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
-            if (ABL != 4) t2_update_B<T, V>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, TWO_A);
-            IO::template st<XB1z>(sa, b[2]);
-            IO::template st<XB1x>(sa, b[0]);
-        }
-        if (ABL != 1) __syncthreads();   // barrier 1: B1(k) rows visible; everybody is done reading sE0 / sB2 of the previous plane
-
-        // ================= phase Y: E1(k), then B2(k-1) ==============================================================
-        IO::template st<XE0z>(sa, en[2]);   // old E(k+1) rows for the next plane's phase X
-        IO::template st<XE0x>(sa, en[0]);
-        if (needE1) {
-            T bzd[V], bxd[V], jv[3][V];
-            IO::template ld<XB1z + DN>(sa, bzd);
-            IO::template ld<XB1x + DN>(sa, bxd);
-            const T bz_pl = __shfl_up_sync(FULL, b[2][V - 1], 1);
-            const T by_pl = __shfl_up_sync(FULL, b[1][V - 1], 1);
+    // ================= phase Y: E1(k), then B2(k-1) ==================================================================
+    IO::template st<XE0z>(sa, en[2]);   // old E(k+1) rows for the next plane's phase X
+    IO::template st<XE0x>(sa, en[0]);
+    if (c.needE1) {
+        T bzd[V], bxd[V], jv[3][V];
+        IO::template ld<XB1z + DN>(sa, bzd);
+        IO::template ld<XB1x + DN>(sa, bxd);
+        const T bz_pl = __shfl_up_sync(FULL, b[2][V - 1], 1);
+        const T by_pl = __shfl_up_sync(FULL, b[1][V - 1], 1);
+        bool use_j = false;
+        if (HAS_J) {
             // J of step s applies to E1(k) on owned planes and on the halo planes that recompute a neighbour's
             // cells (same global coordinates, same J)
             int kgw = a.g.k0 + k;
             if (kgw < 0) kgw += a.g.Nk; else if (kgw >= a.g.Nk) kgw -= a.g.Nk;
-            const bool use_j = HAS_J && j_ijA && (kgw >= a.jbox.lo[2]) && (kgw < a.jbox.hi[2]);
+            use_j = c.j_ijA && (kgw >= a.jbox.lo[2]) && (kgw < a.jbox.hi[2]);
             if (use_j) {
-                const long long pj = plane_of(k) + roff;
+                const long long pj = t2_plane_of(a, k) + c.roff;
                 ldg_vec<T, V>(a.J[0] + pj, jv[0]);
                 ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
                 ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
             }
-            // e0 (= old E(k)) becomes E1(k) in place
-            if (ABL != 4) t2_update_E<T, V>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
         }
-        // now: e0 = E1(k), b = B1(k), b1 = B1(k-1), e1 = E1(k-1), en = old E(k+1)
-        if (needB2) {
-            T ezu[V], exu[V];
-            IO::template ld<XE1z + UP>(sa, ezu);   // E1(k-1) one row up (written in phase Z of the previous plane)
-            IO::template ld<XE1x + UP>(sa, exu);
-            const T ez_nl = __shfl_down_sync(FULL, e1[2][0], 1);
-            const T ey_nl = __shfl_down_sync(FULL, e1[1][0], 1);
-            // b1 (= B1(k-1)) becomes B2(k-1) in place
-            if (ABL != 4) t2_update_B<T, V>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
-            IO::template st<XB2z>(sa, b1[2]);
-            IO::template st<XB2x>(sa, b1[0]);
-        }
-        if (ABL != 1) __syncthreads();   // barrier 2: B2(k-1) rows and old E(k+1) rows visible; everybody is done reading sB1 / sE1
+        // e0 (= old E(k)) becomes E1(k) in place
+        if (ABL != 4) t2_update_E<T, V>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+    }
+    if (c.needB2) {
+        T ezu[V], exu[V];
+        IO::template ld<XE1z + UP>(sa, ezu);   // E1(k-1) one row up (written in phase Z of the previous plane)
+        IO::template ld<XE1x + UP>(sa, exu);
+        const T ez_nl = __shfl_down_sync(FULL, e1[2][0], 1);
+        const T ey_nl = __shfl_down_sync(FULL, e1[1][0], 1);
+        // b1 (= B1(k-1)) becomes B2(k-1) in place
+        if (ABL != 4) t2_update_B<T, V>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
+        IO::template st<XB2z>(sa, b1[2]);
+        IO::template st<XB2x>(sa, b1[0]);
+    }
+    if (ABL != 1) __syncthreads();   // barrier 2: B2(k-1) rows and old E(k+1) rows visible; everybody is done reading sB1 / sE1
 
-        // ================= phase Z: E2(k-1), stores, carry =============================================================
-        if (needE1) {
-            IO::template st<XE1z>(sa, e0[2]);   // E1(k) rows for the next plane's phase Y
-            IO::template st<XE1x>(sa, e0[0]);
-        }
-        if (needE2) {
-            T bzd[V], bxd[V], jv[3][V];
-            IO::template ld<XB2z + DN>(sa, bzd);
-            IO::template ld<XB2x + DN>(sa, bxd);
-            const T bz_pl = __shfl_up_sync(FULL, b1[2][V - 1], 1);
-            const T by_pl = __shfl_up_sync(FULL, b1[1][V - 1], 1);
-            const int kB = k - 1;                          // plane of stage B (an owned plane whenever it is stored)
+    // ================= phase Z: E2(k-1), stores ==========================================================================
+    if (c.needE1) {
+        IO::template st<XE1z>(sa, e0[2]);   // E1(k) rows for the next plane's phase Y
+        IO::template st<XE1x>(sa, e0[0]);
+    }
+    if (c.needE2) {
+        T bzd[V], bxd[V], jv[3][V];
+        IO::template ld<XB2z + DN>(sa, bzd);
+        IO::template ld<XB2x + DN>(sa, bxd);
+        const T bz_pl = __shfl_up_sync(FULL, b1[2][V - 1], 1);
+        const T by_pl = __shfl_up_sync(FULL, b1[1][V - 1], 1);
+        const int kB = k - 1;                          // plane of stage B (an owned plane whenever it is stored)
+        const bool stored = (kB >= c.kb);
+        bool use_j = false;
+        if (HAS_J) {
             const int kgB = a.g.k0 + kB;
-            const bool stored = (kB >= kb) && (kB < ke);
-            const bool use_j = HAS_J && j_ijB && stored && (kgB >= a.jbox.lo[2]) && (kgB < a.jbox.hi[2]);
+            use_j = c.j_ijB && stored && (kgB >= a.jbox.lo[2]) && (kgB < a.jbox.hi[2]);
             if (use_j) {
-                const long long pj = (long long)kB * a.g.plane + roff;
+                const long long pj = (long long)kB * a.g.plane + c.roff;
                 ldg_vec<T, V>(a.J[0] + pj, jv[0]);
                 ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
                 ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
-                if (a.src2 && kgB >= a.s_lo[2] && kgB < a.s_hi[2] && jw >= a.s_lo[1] && jw < a.s_hi[1]) {
-                    const double wy = a.sw[1][jw - a.s_lo[1]], wz = a.sw[2][kgB - a.s_lo[2]];
+                if (a.src2 && kgB >= a.s_lo[2] && kgB < a.s_hi[2] && c.jw >= a.s_lo[1] && c.jw < a.s_hi[1]) {
+                    const double wy = a.sw[1][c.jw - a.s_lo[1]], wz = a.sw[2][kgB - a.s_lo[2]];
 #pragma unroll
                     for (int q = 0; q < V; ++q) {
-                        const int ii = i + q;
+                        const int ii = c.i + q;
                         if (ii >= a.s_lo[0] && ii < a.s_hi[0]) {
                             const T v = (T)dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wy), wz);
                             jv[0][q] = v; jv[1][q] = v; jv[2][q] = v;
@@ -358,25 +310,90 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
                     }
                 }
             }
-            // e1 (= E1(k-1)) becomes E2(k-1) in place
-            if (ABL != 4) t2_update_E<T, V>(e1, b1, b2x, b2y, bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
-            if (out && stored && ABL != 2) {
-                const long long o = (long long)kB * a.g.plane + roff;
-                stg_vec<T, V>(a.Eout[0] + o, e1[0]);
-                stg_vec<T, V>(a.Eout[1] + o, e1[1]);
-                stg_vec<T, V>(a.Eout[2] + o, e1[2]);
-                stg_vec<T, V>(a.Bout[0] + o, b1[0]);
-                stg_vec<T, V>(a.Bout[1] + o, b1[1]);
-                stg_vec<T, V>(a.Bout[2] + o, b1[2]);
-            }
         }
-        // carry: B2(k-1).xy, E1(k), B1(k), old E(k+1)
-#pragma unroll
-        for (int q = 0; q < V; ++q) {
-            b2x[q] = b1[0][q]; b2y[q] = b1[1][q];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { e1[c][q] = e0[c][q]; b1[c][q] = b[c][q]; e0[c][q] = en[c][q]; }
+        // e1 (= E1(k-1)) becomes E2(k-1) in place
+        if (ABL != 4) t2_update_E<T, V>(e1, b1, b2[0], b2[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+        if (c.out && stored && ABL != 2) {
+            const long long o = (long long)kB * a.g.plane + c.roff;
+            stg_vec<T, V>(a.Eout[0] + o, e1[0]);
+            stg_vec<T, V>(a.Eout[1] + o, e1[1]);
+            stg_vec<T, V>(a.Eout[2] + o, e1[2]);
+            stg_vec<T, V>(a.Bout[0] + o, b1[0]);
+            stg_vec<T, V>(a.Bout[1] + o, b1[1]);
+            stg_vec<T, V>(a.Bout[2] + o, b1[2]);
         }
+    }
+}
+
+template <typename T, int BY, bool TWO_A, bool HAS_J, int ABL>
+__device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
+    constexpr int V = VecOf<T>::V;
+    constexpr int TJU = BY - 4;               // output rows per CTA
+    constexpr int TIU = FUSED_OUT_LANES * V;  // output cells per CTA row
+    using IO = SmemIO<T>;
+    static_assert(BY >= 5, "T2 pass needs at least one output row");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int Ni = a.g.Ni, Nj = a.g.Nj;
+    T2Ctx<T> c;
+    c.sa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)((ty + 1) * T2_ROWB + tx * 16);   // the one shared-memory address register
+
+    // ---- roles ---------------------------------------------------------------------------------------------
+    c.i = blockIdx.x * TIU - V + tx * V;                    // first cell of this lane (may be -V or >= Ni)
+    const bool lane_active = (c.i <= Ni);                   // i == Ni: right halo, wrapped to column 0
+    const int iw = (c.i < 0) ? c.i + Ni : ((c.i >= Ni) ? c.i - Ni : c.i);
+    const int j = blockIdx.y * TJU - 2 + ty;
+    const bool row_active = (j <= Nj + 1);
+    c.jw = j % Nj;
+    if (c.jw < 0) c.jw += Nj;
+    // warp-uniform row roles: which stages this row has to produce for the CTA's output rows 2..BY-3
+    c.needB1 = row_active && (ty <= BY - 2);
+    c.needE1 = c.needB1 && (ty >= 1);
+    c.needB2 = c.needE1 && (ty <= BY - 3);
+    c.needE2 = c.needB2 && (ty >= 2) && (j < Nj);
+    c.ldE = lane_active && row_active;
+    c.out = c.needE2 && lane_active && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (c.i < Ni);
+    c.roff = (long long)c.jw * a.g.pitch + (lane_active ? iw : 0);
+    c.kb = a.k_lo + blockIdx.z * a.kc;
+    c.ke = min(c.kb + a.kc, a.k_hi);
+    // J may be non-zero only inside jbox (global coordinates).  Stage A needs it on every cell whose E1 feeds an
+    // output cell, halo lanes / rows included (their wrapped coordinates are tested); stage B only where it stores.
+    c.j_ijA = HAS_J && lane_active && row_active && (iw < a.jbox.hi[0]) && (iw + V > a.jbox.lo[0]) &&
+              (c.jw >= a.jbox.lo[1]) && (c.jw < a.jbox.hi[1]);
+    c.j_ijB = c.j_ijA && c.out;
+
+    // ---- register sets (rotating roles, see t2_plane) ----------------------------------------------------------
+    T eA[3][V], eB[3][V], eC[3][V], bA[3][V], bB[3][V], bC[3][V];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) { eA[q][v] = eB[q][v] = eC[q][v] = (T)0; bA[q][v] = bB[q][v] = bC[q][v] = (T)0; }
+
+    // ---- prologue: the first two ring slots, old E(kb-2) and its rows ------------------------------------------------
+    const int k_first = c.kb - 2;
+    if (ABL != 3) t2_issue_slot<T, BY, 0>(a, c, k_first);
+    cp_async_commit();
+    if (k_first + 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, 1>(a, c, k_first + 1);
+    cp_async_commit();
+    if (c.ldE) {
+        const long long p0 = t2_plane_of(a, k_first) + c.roff;
+        ldg_vec<T, V>(a.Ein[0] + p0, eB[0]);
+        ldg_vec<T, V>(a.Ein[1] + p0, eB[1]);
+        ldg_vec<T, V>(a.Ein[2] + p0, eB[2]);
+    }
+    IO::template st<t2_xq<BY>(0)>(c.sa, eB[2]);
+    IO::template st<t2_xq<BY>(1)>(c.sa, eB[0]);
+    __syncthreads();
+
+#pragma unroll 1
+    for (int k = k_first; k <= c.ke; k += 3) {
+        t2_plane<T, BY, TWO_A, HAS_J, ABL, 0>(a, c, k, eA, eB, eC, bA, bB, bC);
+        if (k + 1 > c.ke) break;
+        t2_plane<T, BY, TWO_A, HAS_J, ABL, 1>(a, c, k + 1, eC, eA, eB, bC, bA, bB);
+        if (k + 2 > c.ke) break;
+        t2_plane<T, BY, TWO_A, HAS_J, ABL, 2>(a, c, k + 2, eB, eC, eA, bB, bC, bA);
     }
     cp_async_wait<0>();
 }
@@ -387,7 +404,7 @@ __device__ __forceinline__ bool t2_meets(int lo, int hi, int blo, int bhi, int N
     return (lo < bhi && hi > blo) || (lo < bhi - N && hi > blo - N) || (lo < bhi + N && hi > blo + N);
 }
 
-template <typename T, int BY, int D, int MINB, bool TWO_A, int ABL = 0>
+template <typename T, int BY, int MINB, bool TWO_A, int ABL = 0>
 __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const FusedT2Args<T> a) {
     constexpr int V = VecOf<T>::V;
     // CTA-uniform: only the few tiles whose footprint (halo included) meets the box where J may be non-zero run
@@ -398,8 +415,8 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     const bool has_j = !a.jbox.empty() && t2_meets(i0, i0 + FUSED_BX * V, a.jbox.lo[0], a.jbox.hi[0], a.g.Ni) &&
                        t2_meets(j0, j0 + BY, a.jbox.lo[1], a.jbox.hi[1], a.g.Nj) &&
                        t2_meets(k0, k1, a.jbox.lo[2], a.jbox.hi[2], a.g.Nk);
-    if (has_j) fused_BE_T2_body<T, BY, D, TWO_A, true, ABL>(a);
-    else fused_BE_T2_body<T, BY, D, TWO_A, false, ABL>(a);
+    if (has_j) fused_BE_T2_body<T, BY, TWO_A, true, ABL>(a);
+    else fused_BE_T2_body<T, BY, TWO_A, false, ABL>(a);
 }
 
 }  // namespace fdtd_b200
