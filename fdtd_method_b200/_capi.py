@@ -38,7 +38,8 @@ class Info(ctypes.Structure):
                 ("pitch", ctypes.c_int64), ("plane", ctypes.c_int64), ("device_bytes", ctypes.c_int64),
                 ("launches", ctypes.c_int64), ("steps_done", ctypes.c_int64),
                 ("fused", ctypes.c_int32), ("rank", ctypes.c_int32), ("nranks", ctypes.c_int32),
-                ("device", ctypes.c_int32)]
+                ("device", ctypes.c_int32), ("temporal", ctypes.c_int32), ("passes_t2", ctypes.c_int64),
+                ("kernel_ns", ctypes.c_int64)]
 
 
 # every entry point include/fdtd_b200.h declares: name -> (restype, argtypes)

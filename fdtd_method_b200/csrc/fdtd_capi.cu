@@ -271,23 +271,24 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
     }
     const int gx = (s->g.Ni + TIU - 1) / TIU;
     const int gy = (s->g.Nj + TJU - 1) / TJU;
-    const int np = a.k_hi - a.k_lo;
+    const int np = a.k_hi - a.k_lo, np2 = a.k_hi2 - a.k_lo2;
     int kc = fused_kc_override();
     if (kc <= 0) {
         // 3 redundant plane iterations per chunk: keep chunks long, but leave enough CTAs for ~8 waves
         kc = 128;
-        while (kc > 16 && (long long)gx * gy * ((np + kc - 1) / kc) < 148LL * MINB * 8) kc /= 2;
+        while (kc > 16 && (long long)gx * gy * ((np + np2 + kc - 1) / kc) < 148LL * MINB * 8) kc /= 2;
     }
     if (kc > np) kc = np;
     a.kc = kc;
-    const int gz = (np + kc - 1) / kc;
+    a.nz1 = (np + kc - 1) / kc;
+    const int gz = a.nz1 + (np2 + kc - 1) / kc;
     if (a.n_half == 2) fused_BE_T2_kernel<T, BY, MINB, true, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
     else fused_BE_T2_kernel<T, BY, MINB, false, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
     return cudaGetLastError();
 }
 
 template <typename T>
-static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int src2, double amp2) {
+static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_lo2, int k_hi2, int src2, double amp2) {
     FusedT2Args<T> a;
     a.g = s->g; a.c = s->c; a.jbox = s->jbox;
     for (int c = 0; c < 3; ++c) {
@@ -298,7 +299,7 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int sr
         a.J[c] = static_cast<const T*>(s->p[JX + c][0]);
         a.s_lo[c] = s->src_lo[c]; a.s_hi[c] = s->src_hi[c]; a.sw[c] = s->d_w[c];
     }
-    a.k_lo = k_lo; a.k_hi = k_hi; a.n_half = n_half;
+    a.k_lo = k_lo; a.k_hi = k_hi; a.k_lo2 = k_lo2; a.k_hi2 = k_hi2; a.n_half = n_half;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     a.src2 = src2; a.amp2 = amp2;
     cudaError_t e;
@@ -494,10 +495,11 @@ static bool t2_disabled_by_env() {
 }
 
 // One launch group over the slab with the halo exchange overlapped: interior planes [H, nk-H) never touch a ghost
-// plane and run while the ring exchange is in flight on the comm stream; the two boundary slabs follow.
+// plane and run while the ring exchange is in flight on the comm stream; the two boundary slabs follow (as one
+// launch when the kernel takes two plane ranges).  launch(lo, hi, lo2, hi2): second range empty when lo2 == hi2.
 template <typename LaunchFn, typename ExchangeFn>
 static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, LaunchFn launch, ExchangeFn exchange) {
-    const int H = 8;   // boundary depth (planes) computed after the halo has landed
+    const int H = 4;   // boundary depth (planes) computed after the halo has landed (>= 2: the T2 pass reads k +- 2)
     fdtd_status_t st;
     if (s->cfg.nranks > 1 && !ghosts_valid && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP)) {
         // north_star (d): halo exchange on its own stream, overlapped with the interior chunks.
@@ -507,13 +509,12 @@ static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, LaunchFn launch, E
         FDTD_CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
         if ((st = exchange(s->comm_stream)) != FDTD_OK) return st;
         FDTD_CUDA_TRY(cudaEventRecord(s->ev_b, s->comm_stream));
-        if ((st = launch(H, s->g.nk - H)) != FDTD_OK) return st;
+        if ((st = launch(H, s->g.nk - H, 0, 0)) != FDTD_OK) return st;
         FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
-        if ((st = launch(0, H)) != FDTD_OK) return st;
-        return launch(s->g.nk - H, s->g.nk);
+        return launch(0, H, s->g.nk - H, s->g.nk);
     }
     if ((st = exchange(s->stream)) != FDTD_OK) return st;
-    return launch(0, s->g.nk);
+    return launch(0, s->g.nk, 0, 0);
 }
 
 // Advance by one step, or by two when the temporally blocked pass applies; *done = steps advanced.
@@ -543,14 +544,19 @@ static fdtd_status_t advance(Solver* s, int remaining, int* done) {
             const int src2 = s->src_active ? 1 : 0;
             const double amp2 = src2 ? s->src_amp[s->src_t] : 0.0;
             st = overlapped(s, s->ghosts_t2_valid,
-                            [&](int lo, int hi) { return DISPATCH(s, launch_t2, s, n_half, lo, hi, src2, amp2); },
+                            [&](int lo, int hi, int lo2, int hi2) { return DISPATCH(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2); },
                             [&](cudaStream_t q) { return exchange_t2(s, q); });
             if (st != FDTD_OK) return st;
             if (src2) { s->src_t++; s->j_stale = true; }
+            s->passes_t2++;
             *done = 2;
         } else {
             st = overlapped(s, s->ghosts_fused_valid,
-                            [&](int lo, int hi) { return DISPATCH(s, launch_fused, s, n_half, lo, hi); },
+                            [&](int lo, int hi, int lo2, int hi2) {
+                                fdtd_status_t r = DISPATCH(s, launch_fused, s, n_half, lo, hi);
+                                if (r == FDTD_OK && hi2 > lo2) r = DISPATCH(s, launch_fused, s, n_half, lo2, hi2);
+                                return r;
+                            },
                             [&](cudaStream_t q) { return exchange_fused(s, q); });
             if (st != FDTD_OK) return st;
         }
@@ -1017,6 +1023,8 @@ fdtd_status_t fdtd_get_info(fdtd_solver_t* h, fdtd_info_t* info) {
     info->steps_done = s->steps_done;
     info->fused = s->fused ? 1 : 0;
     info->rank = s->cfg.rank; info->nranks = s->cfg.nranks; info->device = s->device;
+    info->temporal = s->t2 ? 1 : 0;
+    info->passes_t2 = s->passes_t2;
     return FDTD_OK;
 }
 

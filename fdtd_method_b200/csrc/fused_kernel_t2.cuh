@@ -55,7 +55,9 @@ struct FusedT2Args {
     T* Eout[3];
     T* Bout[3];
     JBox jbox;
-    int k_lo, k_hi;   // local planes [k_lo, k_hi) produced by this launch
+    int k_lo, k_hi;   // local planes [k_lo, k_hi) produced by this launch ...
+    int k_lo2, k_hi2; // ... plus a second range (the other boundary slab of a z-slab rank; empty otherwise)
+    int nz1;          // blockIdx.z < nz1 serves the first range
     int kc;           // planes per CTA chunk
     int n_half;       // stage A: 1 or 2 half steps of B (stage B always applies 2)
     int j_quirk;      // Jx feeds all three components (FDTD_openmp semantics)
@@ -356,8 +358,11 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     c.ldE = lane_active && row_active;
     c.out = c.needE2 && lane_active && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (c.i < Ni);
     c.roff = (long long)c.jw * a.g.pitch + (lane_active ? iw : 0);
-    c.kb = a.k_lo + blockIdx.z * a.kc;
-    c.ke = min(c.kb + a.kc, a.k_hi);
+    {
+        const bool second = (int)blockIdx.z >= a.nz1;
+        c.kb = (second ? a.k_lo2 : a.k_lo) + ((int)blockIdx.z - (second ? a.nz1 : 0)) * a.kc;
+        c.ke = min(c.kb + a.kc, second ? a.k_hi2 : a.k_hi);
+    }
     // J may be non-zero only inside jbox (global coordinates).  Stage A needs it on every cell whose E1 feeds an
     // output cell, halo lanes / rows included (their wrapped coordinates are tested); stage B only where it stores.
     c.j_ijA = HAS_J && lane_active && row_active && (iw < a.jbox.hi[0]) && (iw + V > a.jbox.lo[0]) &&
@@ -410,8 +415,9 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     // CTA-uniform: only the few tiles whose footprint (halo included) meets the box where J may be non-zero run
     // the loop that knows about currents; everybody else runs the lean one.
     const int i0 = blockIdx.x * (FUSED_OUT_LANES * V) - V, j0 = blockIdx.y * (BY - 4) - 2;
-    const int kb = a.k_lo + blockIdx.z * a.kc;
-    const int k0 = a.g.k0 + kb - 2, k1 = a.g.k0 + min(kb + a.kc, a.k_hi) + 1;
+    const bool second = (int)blockIdx.z >= a.nz1;
+    const int kb = (second ? a.k_lo2 : a.k_lo) + ((int)blockIdx.z - (second ? a.nz1 : 0)) * a.kc;
+    const int k0 = a.g.k0 + kb - 2, k1 = a.g.k0 + min(kb + a.kc, second ? a.k_hi2 : a.k_hi) + 1;
     const bool has_j = !a.jbox.empty() && t2_meets(i0, i0 + FUSED_BX * V, a.jbox.lo[0], a.jbox.hi[0], a.g.Ni) &&
                        t2_meets(j0, j0 + BY, a.jbox.lo[1], a.jbox.hi[1], a.g.Nj) &&
                        t2_meets(k0, k1, a.jbox.lo[2], a.jbox.hi[2], a.g.Nk);

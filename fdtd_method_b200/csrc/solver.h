@@ -70,6 +70,7 @@ struct Solver {
 
     int64_t launches = 0;
     int64_t steps_done = 0;
+    int64_t passes_t2 = 0;
 
     void* cur_ptr(int comp) const { return p[comp][(comp < JX) ? cur : 0]; }
 };

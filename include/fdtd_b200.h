@@ -108,6 +108,9 @@ typedef struct fdtd_info {
     int64_t steps_done;
     int32_t fused;             /* 1 if fdtd_step uses the fused E+B pass */
     int32_t rank, nranks, device;
+    int32_t temporal;          /* 1 if fdtd_step(n >= 2) pairs steps into the temporally blocked two-step pass */
+    int64_t passes_t2;         /* two-step passes run so far (each advances 2 steps) */
+    int64_t kernel_ns;         /* reserved */
 } fdtd_info_t;
 
 /* ---- life cycle --------------------------------------------------------- */
