@@ -287,9 +287,50 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
     return cudaGetLastError();
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time dependency on libcuda).
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* off = std::getenv("FDTD_B200_NO_TMA");
+        if (!(off && std::atoi(off) != 0)) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                fn = reinterpret_cast<tmap_encode_fn>(p);
+            cudaGetLastError();
+        }
+    }
+    return fn;
+}
+
+// 3-D tensor map of one component array of generation `gen` (ghost planes included), box = {32*V, by, 1}.
+static bool encode_tmap(const Solver* s, CUtensorMap* tm, int comp, int gen, int by) {
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)s->g.Ni, (cuuint64_t)s->g.Nj, (cuuint64_t)(s->g.nk + 2 * GHOST_PLANES)};
+    const cuuint64_t strides[2] = {(cuuint64_t)s->g.pitch * s->esz, (cuuint64_t)s->g.plane * s->esz};
+    const cuuint32_t box[3] = {(cuuint32_t)(FUSED_BX * (16 / s->esz)), (cuuint32_t)by, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (box[0] > (cuuint32_t)s->g.Ni || by > s->g.Nj) return false;   // no wrap-free tile exists anyway
+    const CUresult r = enc(tm, s->esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                           s->base[comp][gen], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 template <typename T>
 static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_lo2, int k_hi2, int src2, double amp2) {
+    static const int by_of_variant[] = {16, 8, 12};
+    int variant = t2_variant();
+    if (variant < 0 || (variant > 2 && variant < 11) || variant > 15) variant = 0;
     FusedT2Args<T> a;
+    std::memset(&a, 0, sizeof(a));
     a.g = s->g; a.c = s->c; a.jbox = s->jbox;
     for (int c = 0; c < 3; ++c) {
         a.Ein[c] = static_cast<const T*>(s->p[EX + c][s->cur]);
@@ -302,16 +343,16 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
     a.k_lo = k_lo; a.k_hi = k_hi; a.k_lo2 = k_lo2; a.k_hi2 = k_hi2; a.n_half = n_half;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     a.src2 = src2; a.amp2 = amp2;
+    a.use_tma = 1;
+    const int by = variant < 3 ? by_of_variant[variant] : 16;
+    for (int c = 0; c < 3 && a.use_tma; ++c)
+        if (!encode_tmap(s, &a.tmE[c], EX + c, s->cur, by) || !encode_tmap(s, &a.tmB[c], BX + c, s->cur, by)) a.use_tma = 0;
     cudaError_t e;
-    int variant = t2_variant();
-    if (variant < 0) variant = 0;
     switch (variant) {
         default:
         case 0: e = launch_t2_variant<T, 16, 1>(s, a); break;
         case 1: e = launch_t2_variant<T, 8, 2>(s, a); break;
         case 2: e = launch_t2_variant<T, 12, 1>(s, a); break;
-        case 3: e = launch_t2_variant<T, 14, 1>(s, a); break;
-        case 4: e = launch_t2_variant<T, 10, 2>(s, a); break;
 #ifdef FDTD_T2_ABLATE   /* timing experiments only: results are wrong */
         case 11: e = launch_t2_variant<T, 16, 1, 1>(s, a); break;
         case 12: e = launch_t2_variant<T, 16, 1, 2>(s, a); break;

@@ -41,6 +41,8 @@
 // Requires Ni % V == 0 and nk >= 4 (the host falls back to the one-step pass otherwise).
 #pragma once
 
+#include <cuda.h>   // CUtensorMap (the driver entry point is fetched at run time, nothing links against libcuda)
+
 #include "fused_kernel_v2.cuh"
 
 namespace fdtd_b200 {
@@ -66,6 +68,11 @@ struct FusedT2Args {
     int s_lo[3], s_hi[3];      // global box
     const double* sw[3];       // device tables, indexed from s_lo
     double amp2;
+    // TMA: 3-D tensor maps {Ni, Nj, nk + 2*GHOST_PLANES} of the six input arrays, box = {32*V cells, BY rows, 1 plane};
+    // tiles whose footprint needs no periodic wrap in i / j fill their ring slots with six tensor copies per plane
+    int use_tma;
+    alignas(64) CUtensorMap tmE[3];
+    alignas(64) CUtensorMap tmB[3];
 };
 
 // ---- shared-memory plumbing ---------------------------------------------------------------------------------
@@ -75,9 +82,33 @@ constexpr int T2_ROWB = FUSED_BX * 16;   // bytes per exchange / ring row (32 la
 template <int BY> __host__ __device__ constexpr int t2_xq(int q) { return q * (BY + 2) * T2_ROWB; }          // exchange array q, own slot
 template <int BY> __host__ __device__ constexpr int t2_ring0() { return 8 * (BY + 2) * T2_ROWB - T2_ROWB; }   // ring slot 0 comp 0, rel. to sa
 constexpr int T2_D = 3;                  // ring depth = unroll factor of the k loop
+template <int BY> __host__ __device__ constexpr int t2_mbar0() { return (8 * (BY + 2) + T2_D * 6 * BY) * T2_ROWB; }   // absolute
 template <int BY>
 constexpr size_t fused_t2_smem_bytes() {
-    return (size_t)(8 * (BY + 2) + T2_D * 6 * BY) * T2_ROWB;
+    return (size_t)t2_mbar0<BY>() + 64;
+}
+
+// ---- mbarrier / TMA primitives --------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "T2_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra T2_DONE;\n"
+        "bra T2_WAIT;\n"
+        "T2_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int x, int y, int z, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
 template <typename T> struct SmemIO;
@@ -156,7 +187,7 @@ struct T2Ctx {
     unsigned sa;            // shared address of the thread's slot in exchange array 0
     int i, jw;
     int kb, ke;
-    bool needB1, needE1, needB2, needE2, ldE, out, j_ijA, j_ijB;
+    bool needB1, needE1, needB2, needE2, ldE, out, j_ijA, j_ijB, producer;
     long long roff;         // element offset of (jw, iw) inside a plane
 };
 
@@ -197,11 +228,34 @@ __device__ __forceinline__ void t2_issue_slot(const FusedT2Args<T>& a, const T2C
     }
 }
 
+// TMA flavour of the ring fill (tiles that need no periodic wrap in i / j): one thread issues six tensor copies, each
+// a {32*V cells, BY rows, 1 plane} box that lands in the slot with exactly the ring's [row][lane] layout.
+template <typename T, int BY, int SLOT>
+__device__ __forceinline__ void t2_issue_slot_tma(const FusedT2Args<T>& a, const unsigned smem0, const int kk) {
+    constexpr int V = VecOf<T>::V;
+    constexpr int TJU = BY - 4, TIU = FUSED_OUT_LANES * V;
+    constexpr int COMPB = BY * T2_ROWB, SLOTB = 6 * COMPB;
+    const unsigned bar = smem0 + (unsigned)(t2_mbar0<BY>() + 8 * SLOT);
+    const unsigned dst = smem0 + (unsigned)(8 * (BY + 2) * T2_ROWB + SLOT * SLOTB);
+    const int x = blockIdx.x * TIU - V, y = blockIdx.y * TJU - 2;
+    int ke = kk + 1, kb = kk;
+    if (a.g.wrap_k) {
+        if (ke < 0) ke += a.g.nk; else if (ke >= a.g.nk) ke -= a.g.nk;
+        if (kb < 0) kb += a.g.nk; else if (kb >= a.g.nk) kb -= a.g.nk;
+    }
+    mbar_arrive_expect_tx(bar, (unsigned)(6 * COMPB));
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        tma_load_3d(dst + q * COMPB, &a.tmE[q], x, y, ke + GHOST_PLANES, bar);
+        tma_load_3d(dst + (3 + q) * COMPB, &a.tmB[q], x, y, kb + GHOST_PLANES, bar);
+    }
+}
+
 // One plane iteration.  Register sets by role on entry:
 //   en : free -> old E(k+1)           e0 : old E(k) -> E1(k)          e1 : E1(k-1) -> E2(k-1) (stored)
 //   b  : free -> B0(k) -> B1(k)        b1 : B1(k-1) -> B2(k-1) (stored)  b2 : B2(k-2) (x, y used)
-template <typename T, int BY, bool TWO_A, bool HAS_J, int ABL, int SLOT>
-__device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>& c, const int k,
+template <typename T, int BY, bool TWO_A, bool HAS_J, bool TMA, int ABL, int SLOT>
+__device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>& c, const int k, const unsigned parity,
                                          T (&en)[3][VecOf<T>::V], T (&e0)[3][VecOf<T>::V], T (&e1)[3][VecOf<T>::V],
                                          T (&b)[3][VecOf<T>::V], T (&b1)[3][VecOf<T>::V], T (&b2)[3][VecOf<T>::V]) {
     constexpr int V = VecOf<T>::V;
@@ -218,9 +272,16 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     const double cEx = a.c.cEx, cEy = a.c.cEy, cEz = a.c.cEz, cJ = a.c.cJ;
 
     // ================= phase X: B1(k) =============================================================================
-    if (k + T2_D - 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, NEXT>(a, c, k + T2_D - 1);
-    cp_async_commit();
-    cp_async_wait<T2_D - 1>();
+    if (TMA) {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+        if (c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, BY, NEXT>(a, smem0, k + T2_D - 1);
+        mbar_wait(smem0 + (unsigned)(t2_mbar0<BY>() + 8 * SLOT), parity);
+    } else {
+        if (k + T2_D - 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, NEXT>(a, c, k + T2_D - 1);
+        cp_async_commit();
+        cp_async_wait<T2_D - 1>();
+    }
     IO::template ld<RING + 1 * COMPB>(sa, en[1]);
     IO::template ld<RING + 0 * COMPB>(sa, en[0]);
     IO::template ld<RING + 2 * COMPB>(sa, en[2]);
@@ -327,7 +388,7 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     }
 }
 
-template <typename T, int BY, bool TWO_A, bool HAS_J, int ABL>
+template <typename T, int BY, bool TWO_A, bool HAS_J, bool TMA, int ABL>
 __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     constexpr int V = VecOf<T>::V;
     constexpr int TJU = BY - 4;               // output rows per CTA
@@ -356,6 +417,7 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     c.needB2 = c.needE1 && (ty <= BY - 3);
     c.needE2 = c.needB2 && (ty >= 2) && (j < Nj);
     c.ldE = lane_active && row_active;
+    c.producer = TMA && (ty == BY - 1) && (tx == 0);   // the top halo row's warp has no arithmetic of its own
     c.out = c.needE2 && lane_active && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (c.i < Ni);
     c.roff = (long long)c.jw * a.g.pitch + (lane_active ? iw : 0);
     {
@@ -378,10 +440,22 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
 
     // ---- prologue: the first two ring slots, old E(kb-2) and its rows ------------------------------------------------
     const int k_first = c.kb - 2;
-    if (ABL != 3) t2_issue_slot<T, BY, 0>(a, c, k_first);
-    cp_async_commit();
-    if (k_first + 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, 1>(a, c, k_first + 1);
-    cp_async_commit();
+    if (TMA) {
+        const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+        if (c.producer) {
+#pragma unroll
+            for (int d = 0; d < T2_D; ++d) mbar_init(smem0 + (unsigned)(t2_mbar0<BY>() + 8 * d), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            t2_issue_slot_tma<T, BY, 0>(a, smem0, k_first);
+            if (k_first + 1 <= c.ke) t2_issue_slot_tma<T, BY, 1>(a, smem0, k_first + 1);
+        }
+    } else {
+        if (ABL != 3) t2_issue_slot<T, BY, 0>(a, c, k_first);
+        cp_async_commit();
+        if (k_first + 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, 1>(a, c, k_first + 1);
+        cp_async_commit();
+    }
     if (c.ldE) {
         const long long p0 = t2_plane_of(a, k_first) + c.roff;
         ldg_vec<T, V>(a.Ein[0] + p0, eB[0]);
@@ -390,17 +464,19 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     }
     IO::template st<t2_xq<BY>(0)>(c.sa, eB[2]);
     IO::template st<t2_xq<BY>(1)>(c.sa, eB[0]);
-    __syncthreads();
+    __syncthreads();   // (also publishes the mbarrier initialisation to the waiting threads)
 
+    unsigned parity = 0;
 #pragma unroll 1
     for (int k = k_first; k <= c.ke; k += 3) {
-        t2_plane<T, BY, TWO_A, HAS_J, ABL, 0>(a, c, k, eA, eB, eC, bA, bB, bC);
+        t2_plane<T, BY, TWO_A, HAS_J, TMA, ABL, 0>(a, c, k, parity, eA, eB, eC, bA, bB, bC);
         if (k + 1 > c.ke) break;
-        t2_plane<T, BY, TWO_A, HAS_J, ABL, 1>(a, c, k + 1, eC, eA, eB, bC, bA, bB);
+        t2_plane<T, BY, TWO_A, HAS_J, TMA, ABL, 1>(a, c, k + 1, parity, eC, eA, eB, bC, bA, bB);
         if (k + 2 > c.ke) break;
-        t2_plane<T, BY, TWO_A, HAS_J, ABL, 2>(a, c, k + 2, eB, eC, eA, bB, bC, bA);
+        t2_plane<T, BY, TWO_A, HAS_J, TMA, ABL, 2>(a, c, k + 2, parity, eB, eC, eA, bB, bC, bA);
+        parity ^= 1u;
     }
-    cp_async_wait<0>();
+    if (!TMA) cp_async_wait<0>();
 }
 
 // Does the footprint [lo, hi) of a tile (unwrapped coordinates, may stick out of [0, N) by the halo) meet the
@@ -410,10 +486,10 @@ __device__ __forceinline__ bool t2_meets(int lo, int hi, int blo, int bhi, int N
 }
 
 template <typename T, int BY, int MINB, bool TWO_A, int ABL = 0>
-__global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const FusedT2Args<T> a) {
+__global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const __grid_constant__ FusedT2Args<T> a) {
     constexpr int V = VecOf<T>::V;
     // CTA-uniform: only the few tiles whose footprint (halo included) meets the box where J may be non-zero run
-    // the loop that knows about currents; everybody else runs the lean one.
+    // the loop that knows about currents; tiles that need no periodic wrap in i / j load through TMA.
     const int i0 = blockIdx.x * (FUSED_OUT_LANES * V) - V, j0 = blockIdx.y * (BY - 4) - 2;
     const bool second = (int)blockIdx.z >= a.nz1;
     const int kb = (second ? a.k_lo2 : a.k_lo) + ((int)blockIdx.z - (second ? a.nz1 : 0)) * a.kc;
@@ -421,8 +497,14 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     const bool has_j = !a.jbox.empty() && t2_meets(i0, i0 + FUSED_BX * V, a.jbox.lo[0], a.jbox.hi[0], a.g.Ni) &&
                        t2_meets(j0, j0 + BY, a.jbox.lo[1], a.jbox.hi[1], a.g.Nj) &&
                        t2_meets(k0, k1, a.jbox.lo[2], a.jbox.hi[2], a.g.Nk);
-    if (has_j) fused_BE_T2_body<T, BY, TWO_A, true, ABL>(a);
-    else fused_BE_T2_body<T, BY, TWO_A, false, ABL>(a);
+    const bool tma = a.use_tma && ABL == 0 && i0 >= 0 && i0 + FUSED_BX * V <= a.g.Ni && j0 >= 0 && j0 + BY <= a.g.Nj;
+    if (has_j) {
+        fused_BE_T2_body<T, BY, TWO_A, true, false, ABL>(a);   // (rare tiles: keep one flavour)
+    } else if (tma) {
+        fused_BE_T2_body<T, BY, TWO_A, false, true, ABL>(a);
+    } else {
+        fused_BE_T2_body<T, BY, TWO_A, false, false, ABL>(a);
+    }
 }
 
 }  // namespace fdtd_b200
