@@ -3,6 +3,9 @@
 // first 40 steps, :14-87), same "Execution time:" line (:88-91) and the same 10x10 Ex slice print at k = N/2
 // (:125-134); the PML rerun of the reference's never-defined __PML_TEST__ branch (:93-121) is enabled with a
 // third argument "pml".  `--kokkos-slice` prints the YZ slice kokkos_sample.cpp:141-149 prints instead (G10).
+// A third positional argument "1" (what python_script_legend/visualization.py:52 passes) or `--dump [dir]` writes
+// the k = N/2 slice of all six components after every iteration to <dir>/OutFiles_<1..6>/<iter>.csv, the files
+// that script animates (visualization.py:13-23).
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -13,8 +16,11 @@
 #include <string>
 
 #include "FDTD_b200/FDTD_PML.h"
+#include "FDTD_b200/field_dump.h"
 
 using namespace FDTD_b200;
+
+static const char* g_dump_root = nullptr;   // non-null: write the per-iteration slice CSVs
 
 template <class Solver>
 static double run_scenario(Solver& method, const Parameters& params, CurrentParameters& cur_param, int it) {
@@ -44,9 +50,13 @@ static double run_scenario(Solver& method, const Parameters& params, CurrentPara
                     method.get_field(Component::JZ)[index] = value;
                 }
         method.update_fields();
+        if (g_dump_root) write_all_slices_csv(method, t, Axis::Z, -1, g_dump_root);
     }
     method.zeroed_currents();
-    for (int t = cur_time; t < it; t++) method.update_fields();
+    for (int t = cur_time; t < it; t++) {
+        method.update_fields();
+        if (g_dump_root) write_all_slices_csv(method, t, Axis::Z, -1, g_dump_root);
+    }
     method.sync();   // the GPU runs asynchronously; the reference's loop is synchronous
     auto end = std::chrono::high_resolution_clock::now();
     return std::chrono::duration<double>(end - start).count();
@@ -106,7 +116,13 @@ int main(int argc, char* argv[]) {
     for (int a = 1; a < argc; ++a) {
         if (!std::strcmp(argv[a], "pml")) with_pml = true;
         else if (!std::strcmp(argv[a], "--kokkos-slice")) kokkos_slice = true;
+        else if (!std::strcmp(argv[a], "--dump")) {
+            g_dump_root = (a + 1 < argc && argv[a + 1][0] != '-') ? argv[++a] : ".";
+        }
         else if (nargs < 2) pos[nargs++] = argv[a];
+        else if (nargs == 2 && (!std::strcmp(argv[a], "1") || !std::strcmp(argv[a], "0"))) {
+            if (argv[a][0] == '1' && !g_dump_root) g_dump_root = ".";   // visualization.py:52: [exe, N, iters, "1"]
+        }
         else nargs++;
     }
     if (nargs == 0) spherical_wave(32, 100, with_pml, kokkos_slice);

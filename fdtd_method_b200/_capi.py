@@ -59,6 +59,7 @@ SIGNATURES = {
     "fdtd_download": (_i, [_vp, _i, _vp, _sz]),
     "fdtd_scatter": (_i, [_vp, _i, _vp, _vp, _sz]),
     "fdtd_gather": (_i, [_vp, _i, _vp, _vp, _sz]),
+    "fdtd_read_slice": (_i, [_vp, _i, _i, _i, _vp, _sz, ctypes.POINTER(_sz)]),
     "fdtd_set_source": (_i, [_vp, _pi, _pi, _pd, _pd, _pd, _pd, _i]),
     "fdtd_clear_source": (_i, [_vp]),
     "fdtd_sync": (_i, [_vp]),

@@ -538,11 +538,20 @@ static bool t2_disabled_by_env() {
 // One launch group over the slab with the halo exchange overlapped: interior planes [H, nk-H) never touch a ghost
 // plane and run while the ring exchange is in flight on the comm stream; the two boundary slabs follow (as one
 // launch when the kernel takes two plane ranges).  launch(lo, hi, lo2, hi2): second range empty when lo2 == hi2.
+// FDTD_B200_MGPU_DEBUG (timing experiments only, tools/mgpu_probe.py): bit 0 = no overlap, bit 1 = skip the exchange
+// (wrong fields), bits 8.. = boundary depth H.
+static int mgpu_debug() {
+    const char* e = std::getenv("FDTD_B200_MGPU_DEBUG");
+    return e ? std::atoi(e) : 0;
+}
+
 template <typename LaunchFn, typename ExchangeFn>
-static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, LaunchFn launch, ExchangeFn exchange) {
-    const int H = 4;   // boundary depth (planes) computed after the halo has landed (>= 2: the T2 pass reads k +- 2)
+static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, LaunchFn launch, ExchangeFn exchange_in) {
+    const int dbg = (s->cfg.nranks > 1) ? mgpu_debug() : 0;
+    const int H = (dbg >> 8) > 0 ? (dbg >> 8) : 4;   // boundary depth (planes) computed after the halo has landed (>= 2: the T2 pass reads k +- 2)
+    auto exchange = [&](cudaStream_t q) -> fdtd_status_t { return (dbg & 2) ? FDTD_OK : exchange_in(q); };
     fdtd_status_t st;
-    if (s->cfg.nranks > 1 && !ghosts_valid && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP)) {
+    if (s->cfg.nranks > 1 && !ghosts_valid && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP) && !(dbg & 1)) {
         // north_star (d): halo exchange on its own stream, overlapped with the interior chunks.
         //   comm stream   : wait(previous work) -> ring exchange into the ghost planes -> ev_b
         //   compute stream: interior planes [H, nk-H) -> wait(ev_b) -> the two boundary slabs
@@ -822,6 +831,24 @@ static fdtd_status_t gather_impl(Solver* s, int comp, const int64_t* idx, void* 
     return FDTD_OK;
 }
 
+template <typename T>
+static fdtd_status_t slice_impl(Solver* s, int comp, int axis, int local_index, int n0, int n1, void* host) {
+    const size_t bytes = (size_t)n0 * n1 * sizeof(T);
+    fdtd_status_t st = ensure_stage(s, bytes);
+    if (st != FDTD_OK) return st;
+    const long long total = (long long)n0 * n1;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    slice_kernel<T><<<(int)blocks, 256, 0, s->stream>>>(static_cast<const T*>(s->cur_ptr(comp)), s->g, axis, local_index, n0, n1,
+                                                        static_cast<T*>(s->d_stage));
+    FDTD_CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    FDTD_CUDA_TRY(cudaMemcpyAsync(s->h_stage, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    std::memcpy(host, s->h_stage, bytes);
+    return FDTD_OK;
+}
+
 }  // namespace fdtd_b200
 
 // ======================================================================================================
@@ -992,6 +1019,30 @@ fdtd_status_t fdtd_gather(fdtd_solver_t* h, int comp, const int64_t* idx, void* 
         if (idx[t] < 0 || idx[t] >= total) return fail(FDTD_ERR_BAD_ARGUMENT, "gather: index out of range");
     if (comp >= BX && comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
     return (s->dtype == FDTD_F32) ? gather_impl<float>(s, comp, idx, values, n) : gather_impl<double>(s, comp, idx, values, n);
+}
+
+fdtd_status_t fdtd_read_slice(fdtd_solver_t* h, int comp, int axis, int index, void* host, size_t capacity, size_t* count_out) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if ((st = check_component(comp)) != FDTD_OK) return st;
+    if (count_out) *count_out = 0;
+    const int N[3] = {s->g.Ni, s->g.Nj, s->g.Nk};
+    if (axis < 0 || axis > 2 || index < 0 || index >= N[axis]) return fail(FDTD_ERR_BAD_ARGUMENT, "read_slice: axis / index out of range");
+    int n0, n1, local = index;
+    if (axis == 2) {
+        n0 = s->g.Ni; n1 = s->g.Nj; local = index - s->g.k0;
+        if (local < 0 || local >= s->g.nk) return FDTD_OK;   // another rank owns this plane: nothing to copy here
+    } else {
+        n0 = (axis == 1) ? s->g.Ni : s->g.Nj; n1 = s->g.nk;
+    }
+    const size_t n = (size_t)n0 * n1;
+    if (!host || capacity < n) return fail(FDTD_ERR_BAD_ARGUMENT, "read_slice: host buffer too small");
+    if (comp >= BX && comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
+    if (comp >= JX && (st = materialize_J(s)) != FDTD_OK) return st;
+    st = (s->dtype == FDTD_F32) ? slice_impl<float>(s, comp, axis, local, n0, n1, host) : slice_impl<double>(s, comp, axis, local, n0, n1, host);
+    if (st == FDTD_OK && count_out) *count_out = n;
+    return st;
 }
 
 fdtd_status_t fdtd_set_source(fdtd_solver_t* h, const int lo[3], const int hi[3], const double* wx, const double* wy,

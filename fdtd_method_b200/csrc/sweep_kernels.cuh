@@ -411,6 +411,22 @@ __global__ void gather_kernel(const T* __restrict__ f, Geom g, const long long* 
     vals[t] = f[(long long)k * g.plane + (r / g.Ni) * g.pitch + (r % g.Ni)];
 }
 
+// Dense 2-D slice at a fixed coordinate along `axis` (fdtd_read_slice): the per-step field dump that feeds
+// python_script_legend/visualization.py:13-23 (OutFiles_<n>/<iter>.csv).  out is row-major [n1][n0] with
+// (n0, n1) = (Ni, Nj) for axis 2 (local plane `index`), (Ni, nk) for axis 1, (Nj, nk) for axis 0.
+template <typename T>
+__global__ void slice_kernel(const T* __restrict__ f, Geom g, int axis, int index, int n0, int n1, T* __restrict__ out) {
+    const long long total = (long long)n0 * n1;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(t % n0), b = (int)(t / n0);
+        long long o;
+        if (axis == 2) o = (long long)index * g.plane + (long long)b * g.pitch + a;
+        else if (axis == 1) o = (long long)b * g.plane + (long long)index * g.pitch + a;
+        else o = (long long)b * g.plane + (long long)a * g.pitch + index;
+        out[t] = f[o];
+    }
+}
+
 // Device-resident current source (fdtd_set_source): J = ((amp*wx)*wy)*wz on a box, the product order of
 // perf-tests/sample/sample.cpp:26-31; `zero` writes +0.0 instead (source expired / zeroed_currents on a box).
 struct SourceArgs {

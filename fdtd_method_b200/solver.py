@@ -127,6 +127,39 @@ class FDTD:
         _capi.check(_capi.lib().fdtd_gather(self._h, int(comp), idx.ctypes.data, vals.ctypes.data, idx.size))
         return vals
 
+    def read_slice(self, comp, axis: int, index: int) -> np.ndarray | None:
+        """2-D slice at a fixed GLOBAL coordinate along ``axis`` (0 = i, 1 = j, 2 = k), extracted on the device.
+        axis 2 -> [Nj, Ni] (None on a rank that does not own the plane); axis 1 -> [nk_local, Ni]; axis 0 -> [nk_local, Nj]."""
+        nk, Nj, Ni = self.local_shape
+        shape = {2: (Nj, Ni), 1: (nk, Ni), 0: (nk, Nj)}.get(int(axis))
+        if shape is None:
+            raise TypeError("axis must be 0, 1 or 2")
+        out = np.empty(shape, dtype=self.dtype)
+        n = ctypes.c_size_t()
+        _capi.check(_capi.lib().fdtd_read_slice(self._h, int(comp), int(axis), int(index), out.ctypes.data, out.size, ctypes.byref(n)))
+        return out if n.value == out.size else None
+
+    def dump_slices(self, iteration: int, root: str = ".", axis: int = 2, index: int | None = None, components=range(6)) -> list[str]:
+        """Write ``<root>/OutFiles_<c+1>/<iteration>.csv`` for each component (Ex=1 ... Bz=6): the ';'-separated
+        per-iteration slice files python_script_legend/visualization.py:10-23,34 of the reference reads.  The rank
+        that owns the plane writes (axis 2); returns the paths written."""
+        import os
+        if index is None:
+            index = (self.parameters.Ni, self.parameters.Nj, self.parameters.Nk)[axis] // 2
+        paths = []
+        for c in components:
+            a = self.read_slice(c, axis, index)
+            if a is None:
+                continue
+            d = os.path.join(root, f"OutFiles_{int(c) + 1}")
+            os.makedirs(d, exist_ok=True)
+            path = os.path.join(d, f"{int(iteration)}.csv")
+            with open(path, "w") as fh:
+                for row in a:
+                    fh.write(";".join(repr(float(v)) for v in row) + "\n")
+            paths.append(path)
+        return paths
+
     def set_source(self, lo, hi, wx, wy, wz, amp) -> None:
         """Device-resident current source: J = ((amp[t]*wx)*wy)*wz on [lo, hi) before step t."""
         lo_a = (ctypes.c_int * 3)(*[int(v) for v in lo])

@@ -80,6 +80,17 @@ private:
     }
 
     FP read(std::size_t i) {
+        // A handful of probe reads after a step (the 10x10 slice of sample.cpp:125-134) are served by sparse
+        // device gathers; a caller that keeps reading (Test_FDTD::get_max_abs_error walks a whole line or more)
+        // gets one dense download instead.
+        if (!host_valid_ && sparse_reads_ < kSparseReadLimit) {
+            flush();
+            ++sparse_reads_;
+            const int64_t idx = static_cast<int64_t>(i);
+            FP v = 0;
+            check(fdtd_gather(h_, comp_, &idx, &v, 1));
+            return v;
+        }
         ensure_host();
         return host_[i];
     }
@@ -120,7 +131,7 @@ private:
         log_idx_.clear(); log_val_.clear();
     }
 
-    void invalidate() { host_valid_ = false; }
+    void invalidate() { host_valid_ = false; sparse_reads_ = 0; }
 
     fdtd_solver_t* h_ = nullptr;
     int comp_ = 0;
@@ -128,6 +139,8 @@ private:
     std::vector<FP> host_;
     bool host_valid_ = false;
     bool dense_dirty_ = false;
+    static constexpr std::size_t kSparseReadLimit = 256;
+    std::size_t sparse_reads_ = 0;
     std::vector<int64_t> log_idx_;
     std::vector<FP> log_val_;
 };
@@ -176,6 +189,19 @@ public:
         for (int c = 0; c < 6; ++c) fields_[c].invalidate();
     }
     void sync() { Field::check(fdtd_sync(h_)); }          // Kokkos::fence() equivalent
+    // Dense 2-D slice at a fixed coordinate along `axis` (0 = i, 1 = j, 2 = k), extracted on the device
+    // (row-major [n1][n0]: axis 2 -> Nj x Ni, axis 1 -> Nk x Ni, axis 0 -> Nk x Nj).
+    std::vector<FP> read_slice(Component this_field, Axis axis, int index) {
+        const int c = static_cast<int>(this_field), a = static_cast<int>(axis);
+        fields_[c].flush();
+        const std::size_t n0 = (a == 0) ? parameters.Nj : parameters.Ni, n1 = (a == 2) ? parameters.Nj : parameters.Nk;
+        std::vector<FP> out(n0 * n1);
+        std::size_t got = 0;
+        Field::check(fdtd_read_slice(h_, c, a, index, out.data(), out.size(), &got));
+        out.resize(got);
+        return out;
+    }
+    const Parameters& get_parameters() const { return parameters; }
     fdtd_solver_t* handle() { return h_; }
 
 protected:

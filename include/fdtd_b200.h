@@ -155,6 +155,15 @@ fdtd_status_t fdtd_download(fdtd_solver_t* s, int component, void* host, size_t 
 fdtd_status_t fdtd_scatter(fdtd_solver_t* s, int component, const int64_t* idx, const void* values, size_t n);
 fdtd_status_t fdtd_gather(fdtd_solver_t* s, int component, const int64_t* idx, void* values, size_t n);
 
+/* Dense 2-D slice at a fixed GLOBAL coordinate `index` along `axis` (0 = i, 1 = j, 2 = k), extracted on the
+ * device: the per-iteration field dump behind python_script_legend/visualization.py:13-23 (one CSV per
+ * iteration and component).  Row-major [n1][n0] elements of the solver dtype with
+ *   axis 2: (n0, n1) = (Ni, Nj) when this rank owns plane `index`, otherwise nothing is copied;
+ *   axis 1: (n0, n1) = (Ni, k_end - k_begin);   axis 0: (n0, n1) = (Nj, k_end - k_begin).
+ * *count_out = elements written (0 on a rank that does not own the plane). */
+fdtd_status_t fdtd_read_slice(fdtd_solver_t* s, int component, int axis, int index, void* host, size_t capacity,
+                              size_t* count_out);
+
 /* Device-resident current source (so the sample scenario never crosses PCIe):
  *   J{x,y,z}(i,j,k) = ((amp[t] * wx[i-lo_i]) * wy[j-lo_j]) * wz[k-lo_k]   on the box [lo, hi)
  * written before step t (t counted from this call), for t < n_amp.  The product order is the

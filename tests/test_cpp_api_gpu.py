@@ -62,3 +62,37 @@ def test_sample_clone_kokkos_slice(cpp_bins, golden_dir):
     assert _slice_rows(r.stdout) == [[f"{v:.5f}" for v in row] for row in yz]
     # first row of ./kokkos_sample (32,100)
     assert _slice_rows(r.stdout)[0][:3] == ["0.04722", "0.00665", "-0.01068"]
+
+
+def test_sample_clone_writes_the_visualisation_csvs(cpp_bins, golden_dir, tmp_path):
+    """`./sample N iters 1` (the argv python_script_legend/visualization.py:52 passes) writes
+    OutFiles_<1..6>/<iter>.csv, ';'-separated k = N/2 slices; the last Ex file holds the golden slice values."""
+    r = subprocess.run([os.path.join(cpp_bins, "sample_b200"), "32", "100", "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=300, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout
+    for c in range(1, 7):
+        files = sorted(os.listdir(tmp_path / f"OutFiles_{c}"), key=lambda f: int(f.split(".")[0]))
+        assert files == [f"{t}.csv" for t in range(100)]
+    rows = [[float(v) for v in line.split(";")] for line in open(tmp_path / "OutFiles_1" / "99.csv").read().split()]
+    assert len(rows) == 32 and all(len(row) == 32 for row in rows)
+    per = json.load(open(os.path.join(golden_dir, "sample_32_100_periodic.json")))["slice_EX_xy"]
+    got = [[f"{rows[j][i]:.5f}" for i in range(11, 21)] for j in range(11, 21)]
+    assert got == [[f"{v:.5f}" for v in row] for row in per]
+    # the slice printed on stdout is the same data
+    assert _slice_rows(r.stdout) == got
+
+
+@pytest.mark.parametrize("images", [1, 2])
+def test_coarray_program(cpp_bins, golden_dir, gpu_count, images):
+    """coarray/fdtd.F90's program (one image per GPU): banner lines and the 10x10 Ex slice, which for
+    the 32^3 x 100 scenario is the slice the real reference's sample prints (same source, same steps)."""
+    if gpu_count < images:
+        pytest.skip(f"needs {images} GPUs")
+    r = subprocess.run([os.path.join(cpp_bins, "fdtd_coarray_b200"), "--images", str(images), "32", "32", "32", "100"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    lines = r.stdout.splitlines()
+    assert f"Running on {images} images" in lines
+    assert any(l.startswith("Total execution time: ") and l.endswith(" seconds") for l in lines)
+    per = json.load(open(os.path.join(golden_dir, "sample_32_100_periodic.json")))["slice_EX_xy"]
+    assert _slice_rows(r.stdout) == [[f"{v:.5f}" for v in row] for row in per]

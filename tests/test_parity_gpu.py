@@ -267,6 +267,30 @@ def test_scatter_gather_and_zeroed_currents():
     assert g.get_field(0).size() == Ni * Nj * Nk
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_read_slice_and_dump(dtype, tmp_path):
+    """fdtd_read_slice: device-side extraction of i / j / k slices equals slicing the dense download, after an odd
+    number of steps (deferred B half step pending) and for J; dump_slices writes the OutFiles_<n>/<iter>.csv feed."""
+    Ni, Nj, Nk = 24, 10, 7
+    o, g = make_pair(Ni, Nj, Nk, dtype=dtype)
+    f = seeded_fields(11, (Nk, Nj, Ni), dtype=dtype, same_j=False)
+    load_both(o, g, f)
+    o.step(3); g.step(3)
+    for c in range(9):
+        full = o.field(c)
+        assert np.array_equal(g.read_slice(c, 2, 4), full[4]), c
+        assert np.array_equal(g.read_slice(c, 1, 9), full[:, 9, :]), c
+        assert np.array_equal(g.read_slice(c, 0, 23), full[:, :, 23]), c
+    with pytest.raises(TypeError):
+        g.read_slice(0, 2, Nk)
+    paths = g.dump_slices(3, root=str(tmp_path))
+    assert [os.path.relpath(p, tmp_path) for p in paths] == [f"OutFiles_{c}/3.csv" for c in range(1, 7)]
+    rows = np.array([[float(v) for v in line.split(";")] for line in open(paths[4]).read().split()])
+    assert np.array_equal(rows, o.field(4)[Nk // 2].astype(np.float64))
+    o.step(1); g.step(1)
+    assert_bit_equal(o, g, what="stepping after slice reads")
+
+
 def test_errors_match_reference_semantics():
     with pytest.raises(ValueError, match="invalid parameters"):      # FDTD.cpp:5-7
         fb.FDTD(params(0, 4, 4), 0.2)
