@@ -184,7 +184,7 @@ def run_reference_arm(a):
         "e2e": {"value": r["value"], "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(a, world, note=None):
@@ -362,13 +362,28 @@ def run_ours(a):
                 line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the checker is optional for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "Gcell-updates/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     g.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the process's original stdout; everything else printed to fd 1 by libraries
+    (NCCL's version banner, torchrun notices) was re-routed to stderr in main()."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -390,7 +405,7 @@ def main():
         import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=_JSON_OUT))   # the children print the JSON line to our real stdout
     run_ours(a)
 
 

@@ -170,7 +170,7 @@ static cudaError_t launch_fused_variant(Solver* s, FusedArgs<T>& a) {
     if (kc > np) kc = np;
     a.kc = kc;
     const int gz = (np + kc - 1) / kc;
-    fused_BE_kernel<T, BY, RJ, MINB><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), 0, s->stream>>>(a);
+    fused_BE_kernel<T, BY, RJ, MINB><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), 0, s->launch_stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -197,7 +197,7 @@ static cudaError_t launch_fused2_variant(Solver* s, FusedArgs<T>& a) {
     if (kc > np) kc = np;
     a.kc = kc;
     const int gz = (np + kc - 1) / kc;
-    fused_BE2_kernel<T, BY, PF, D, MINB><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
+    fused_BE2_kernel<T, BY, PF, D, MINB><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -282,8 +282,8 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
     a.kc = kc;
     a.nz1 = (np + kc - 1) / kc;
     const int gz = a.nz1 + (np2 + kc - 1) / kc;
-    if (a.n_half == 2) fused_BE_T2_kernel<T, BY, MINB, true, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
-    else fused_BE_T2_kernel<T, BY, MINB, false, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->stream>>>(a);
+    if (a.n_half == 2) fused_BE_T2_kernel<T, BY, MINB, true, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
+    else fused_BE_T2_kernel<T, BY, MINB, false, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -538,8 +538,16 @@ static bool t2_disabled_by_env() {
 // One launch group over the slab with the halo exchange overlapped: interior planes [H, nk-H) never touch a ghost
 // plane and run while the ring exchange is in flight on the comm stream; the two boundary slabs follow (as one
 // launch when the kernel takes two plane ranges).  launch(lo, hi, lo2, hi2): second range empty when lo2 == hi2.
+//
+// Three streams.  The pass kernels own every SM (one 512-thread CTA holds the whole register file), so (1) the comm
+// stream has the highest priority: NCCL's few CTAs are dispatched to the first SMs that free up instead of behind
+// the interior launch's ~1500 pending CTAs, and the planes land early in the pass; (2) the boundary slabs go to a
+// third, normal-priority stream: they read only the input generation and write planes the interior launch does not,
+// so they are independent of it, and their short CTAs are dispatched when the interior launch has no CTA left to
+// issue -- they fill its partial last wave instead of adding launches after it.
 // FDTD_B200_MGPU_DEBUG (timing experiments only, tools/mgpu_probe.py): bit 0 = no overlap, bit 1 = skip the exchange
-// (wrong fields), bits 8.. = boundary depth H.
+// (wrong fields), bit 2 = boundary slabs on the compute stream (after the interior launch), bit 3 = comm stream without
+// priority (read when the solver is created), bits 8.. = boundary depth H.
 static int mgpu_debug() {
     const char* e = std::getenv("FDTD_B200_MGPU_DEBUG");
     return e ? std::atoi(e) : 0;
@@ -548,20 +556,33 @@ static int mgpu_debug() {
 template <typename LaunchFn, typename ExchangeFn>
 static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, LaunchFn launch, ExchangeFn exchange_in) {
     const int dbg = (s->cfg.nranks > 1) ? mgpu_debug() : 0;
-    const int H = (dbg >> 8) > 0 ? (dbg >> 8) : 4;   // boundary depth (planes) computed after the halo has landed (>= 2: the T2 pass reads k +- 2)
+    const int H = (dbg >> 8) > 0 ? (dbg >> 8) : 2;   // boundary depth (planes) computed after the halo has landed (>= 2: the T2 pass reads k +- 2)
     auto exchange = [&](cudaStream_t q) -> fdtd_status_t { return (dbg & 2) ? FDTD_OK : exchange_in(q); };
     fdtd_status_t st;
-    if (s->cfg.nranks > 1 && !ghosts_valid && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP) && !(dbg & 1)) {
+    s->launch_stream = s->stream;
+    if (s->cfg.nranks > 1 && !ghosts_valid && H >= 2 && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP) && !(dbg & 1)) {
         // north_star (d): halo exchange on its own stream, overlapped with the interior chunks.
-        //   comm stream   : wait(previous work) -> ring exchange into the ghost planes -> ev_b
-        //   compute stream: interior planes [H, nk-H) -> wait(ev_b) -> the two boundary slabs
+        //   comm stream    : wait(previous work) -> ring exchange into the ghost planes -> ev_b
+        //   compute stream : interior planes [H, nk-H) ........................................ -> wait(ev_c)
+        //   boundary stream: wait(previous work, ev_b) -> the two boundary slabs -> ev_c
         FDTD_CUDA_TRY(cudaEventRecord(s->ev_a, s->stream));
         FDTD_CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
         if ((st = exchange(s->comm_stream)) != FDTD_OK) return st;
         FDTD_CUDA_TRY(cudaEventRecord(s->ev_b, s->comm_stream));
         if ((st = launch(H, s->g.nk - H, 0, 0)) != FDTD_OK) return st;
-        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
-        return launch(0, H, s->g.nk - H, s->g.nk);
+        if (dbg & 4) {
+            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
+            return launch(0, H, s->g.nk - H, s->g.nk);
+        }
+        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->bnd_stream, s->ev_a, 0));
+        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->bnd_stream, s->ev_b, 0));
+        s->launch_stream = s->bnd_stream;
+        st = launch(0, H, s->g.nk - H, s->g.nk);
+        s->launch_stream = s->stream;
+        if (st != FDTD_OK) return st;
+        FDTD_CUDA_TRY(cudaEventRecord(s->ev_c, s->bnd_stream));
+        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_c, 0));
+        return FDTD_OK;
     }
     if ((st = exchange(s->stream)) != FDTD_OK) return st;
     return launch(0, s->g.nk, 0, 0);
@@ -652,6 +673,8 @@ static void destroy_impl(Solver* s) {
     if (s->ev_t1) cudaEventDestroy(s->ev_t1);
     if (s->ev_a) cudaEventDestroy(s->ev_a);
     if (s->ev_b) cudaEventDestroy(s->ev_b);
+    if (s->ev_c) cudaEventDestroy(s->ev_c);
+    if (s->bnd_stream) cudaStreamDestroy(s->bnd_stream);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -731,10 +754,18 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
     auto bail = [&](fdtd_status_t code) { std::string keep = g_err; destroy_impl(s); g_err = keep; return code; };
 
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
-    if (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
+    {
+        int prio_lo = 0, prio_hi = 0;   // numerically lower = higher priority
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        { const char* e = std::getenv("FDTD_B200_MGPU_DEBUG"); if (e && (std::atoi(e) & 8)) prio_hi = prio_lo; }   // bit 3 (read here): no priority
+        if (cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
+    }
+    if (cudaStreamCreateWithFlags(&s->bnd_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
+    s->launch_stream = s->stream;
     cudaEventCreate(&s->ev_t0); cudaEventCreate(&s->ev_t1);
     cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_c, cudaEventDisableTiming);
 
     // The fused pass serves the periodic solver with vector-aligned rows; everything else runs the two sweeps.
     const int V = (int)(16 / s->esz);
@@ -962,8 +993,11 @@ fdtd_status_t fdtd_upload(fdtd_solver_t* h, int comp, const void* host, size_t c
     } else {
         jbox_full(s);
     }
-    FDTD_CUDA_TRY(cudaMemcpy2DAsync(s->cur_ptr(comp), (size_t)s->g.pitch * s->esz, host, (size_t)s->g.Ni * s->esz,
-                                    (size_t)s->g.Ni * s->esz, (size_t)s->g.Nj * s->g.nk, cudaMemcpyHostToDevice, s->stream));
+    if (s->g.pitch == s->g.Ni)   // unpadded rows: the slab is one contiguous block, like the reference's flat vector
+        FDTD_CUDA_TRY(cudaMemcpyAsync(s->cur_ptr(comp), host, expect * s->esz, cudaMemcpyHostToDevice, s->stream));
+    else
+        FDTD_CUDA_TRY(cudaMemcpy2DAsync(s->cur_ptr(comp), (size_t)s->g.pitch * s->esz, host, (size_t)s->g.Ni * s->esz,
+                                        (size_t)s->g.Ni * s->esz, (size_t)s->g.Nj * s->g.nk, cudaMemcpyHostToDevice, s->stream));
     FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
     return FDTD_OK;
 }
@@ -977,8 +1011,11 @@ fdtd_status_t fdtd_download(fdtd_solver_t* h, int comp, void* host, size_t count
     if (!host || count != expect) return fail(FDTD_ERR_BAD_ARGUMENT, "download: count must equal Ni*Nj*(k_end-k_begin)");
     // only B carries a deferred half step; E(n+1) is already final after the pass
     if (comp >= BX && comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
-    FDTD_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)s->g.Ni * s->esz, s->cur_ptr(comp), (size_t)s->g.pitch * s->esz,
-                                    (size_t)s->g.Ni * s->esz, (size_t)s->g.Nj * s->g.nk, cudaMemcpyDeviceToHost, s->stream));
+    if (s->g.pitch == s->g.Ni)
+        FDTD_CUDA_TRY(cudaMemcpyAsync(host, s->cur_ptr(comp), expect * s->esz, cudaMemcpyDeviceToHost, s->stream));
+    else
+        FDTD_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)s->g.Ni * s->esz, s->cur_ptr(comp), (size_t)s->g.pitch * s->esz,
+                                        (size_t)s->g.Ni * s->esz, (size_t)s->g.Nj * s->g.nk, cudaMemcpyDeviceToHost, s->stream));
     FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
     return FDTD_OK;
 }

@@ -39,8 +39,10 @@ struct Solver {
     int64_t device_bytes = 0;
 
     cudaStream_t stream = nullptr;
-    cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr;
+    cudaStream_t comm_stream = nullptr;   // halo exchange (highest priority: NCCL's CTAs take the first SMs that free up)
+    cudaStream_t bnd_stream = nullptr;    // boundary slabs of an overlapped pass (fill the interior launch's tail wave)
+    cudaStream_t launch_stream = nullptr; // where the pass kernels of the current launch group go (stream or bnd_stream)
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
 
     // Deferred trailing B half step: after update_fields() the device holds E(n+1) and B(n+1/2);
     // the missing half step is merged into the next step's leading half step (B = (B+h)+h) or applied

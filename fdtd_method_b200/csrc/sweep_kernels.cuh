@@ -119,6 +119,29 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
             carry_ok = false;      // this cell belongs to the mode-1 launch
             continue;
         }
+
+        bool row_main = jrow_main;
+        double dcz = 1.0, c2z = 0.0;
+        if (PML) {
+            const int kg = a.g.k0 + k;
+            row_main = row_main && (kg >= a.p.lo[2] && kg < a.p.hi[2]);
+            dcz = a.p.decay[2][kg];
+            c2z = a.p.coef2[2][kg];
+        }
+        bool any_pml = false, all_pml = PML;
+        if (PML) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const bool cell_pml = !(row_main && col_main[e]);
+                any_pml = any_pml || (e < nvalid && cell_pml);
+                all_pml = all_pml && (e >= nvalid || cell_pml);
+            }
+            if (all_pml && !a.do_pml) {   // deferred half step: shell cells stay as they are
+                carry_ok = false;
+                continue;
+            }
+            any_pml = any_pml && a.do_pml;
+        }
         if (!carry_ok) {
             ldv(Ex + o, ex);
             ldv(Ey + o, ey);
@@ -133,23 +156,10 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
         ldv(Ex + pk + rown + i0, exj);
         const double ez_r = lds1(Ez + pk + row + cn);
         const double ey_r = lds1(Ey + pk + row + cn);
-        ldv(Bx + o, bx);
-        ldv(By + o, by);
-        ldv(Bz + o, bz);
-
-        bool row_main = jrow_main;
-        double dcz = 1.0, c2z = 0.0;
-        if (PML) {
-            const int kg = a.g.k0 + k;
-            row_main = row_main && (kg >= a.p.lo[2] && kg < a.p.hi[2]);
-            dcz = a.p.decay[2][kg];
-            c2z = a.p.coef2[2][kg];
-        }
-        bool any_pml = false;
-        if (PML) {
-#pragma unroll
-            for (int e = 0; e < V; ++e) any_pml = any_pml || (e < nvalid && !(row_main && col_main[e]));
-            any_pml = any_pml && a.do_pml;
+        if (!all_pml) {   // a shell cell's B is the sum of its split fields (FDTD_PML.cpp:197-199): the old value is never read
+            ldv(Bx + o, bx);
+            ldv(By + o, by);
+            ldv(Bz + o, bz);
         }
         double sxy[V], sxz[V], syx[V], syz[V], szx[V], szy[V];
         if (PML && any_pml) {
@@ -303,18 +313,6 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
         ldv(Bx + pk + rowp + i0, bxj);
         const double bz_l = lds1(Bz + pk + row + cp);
         const double by_l = lds1(By + pk + row + cp);
-        ldv(Ex + o, e_x);
-        ldv(Ey + o, e_y);
-        ldv(Ez + o, e_z);
-
-        const bool use_j = j_ij && (kg >= a.jbox.lo[2] && kg < a.jbox.hi[2]);
-        double jx[V], jy[V], jz[V];
-        if (use_j) {
-            ldv(Jx + o, jx);
-            ldv(Jy + o, jy);
-            ldv(Jz + o, jz);
-        }
-
         bool row_main = jrow_main;
         double dcz = 1.0, c2z = 0.0;
         if (PML) {
@@ -322,10 +320,27 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
             dcz = a.p.decay[2][kg];
             c2z = a.p.coef2[2][kg];
         }
-        bool any_pml = false;
+        bool any_pml = false, all_pml = PML;
         if (PML) {
 #pragma unroll
-            for (int e = 0; e < V; ++e) any_pml = any_pml || (e < nvalid && !(row_main && col_main[e]));
+            for (int e = 0; e < V; ++e) {
+                const bool cell_pml = !(row_main && col_main[e]);
+                any_pml = any_pml || (e < nvalid && cell_pml);
+                all_pml = all_pml && (e >= nvalid || cell_pml);
+            }
+        }
+        if (!all_pml) {   // a shell cell's E is the sum of its split fields (FDTD_PML.cpp:128-130): the old value is never read
+            ldv(Ex + o, e_x);
+            ldv(Ey + o, e_y);
+            ldv(Ez + o, e_z);
+        }
+
+        const bool use_j = !all_pml && j_ij && (kg >= a.jbox.lo[2] && kg < a.jbox.hi[2]);
+        double jx[V], jy[V], jz[V];
+        if (use_j) {
+            ldv(Jx + o, jx);
+            ldv(Jy + o, jy);
+            ldv(Jz + o, jz);
         }
         double sxy[V], sxz[V], syx[V], syz[V], szx[V], szy[V];
         if (PML && any_pml) {

@@ -32,6 +32,8 @@ def main():
         ((33, 9, 11), None, True, np.float64, 5),              # odd Ni -> two-sweep kernels
         ((32, 16, 32 * world), None, True, np.float64, 5),     # 32 planes per rank: overlapped halo exchange path
         ((64, 48, 40 * world), 0.1, False, np.float64, 5),     # PML interior/shell split on slabs
+        ((32, 16, 8 * world), None, True, np.float64, 6),      # smallest slab that takes the overlapped path (H = 2)
+        ((64, 24, 12 * world), None, True, np.float32, 5),     # overlapped path, fp32
     ]
     failures = 0
     for shape, pml, fusion, dtype, steps in cases:

@@ -44,8 +44,9 @@ def main():
     for c in range(6):
         g.upload(c, plane)
     rows = []
-    variants = [("overlap", 0), ("no-overlap", 1), ("overlap, exchange skipped", 2), ("single launch, exchange skipped", 3),
-                ("overlap H=2", 2 << 8), ("overlap H=8", 8 << 8)]
+    variants = [("3 streams H=2 (default)", 0), ("3 streams H=4", 4 << 8), ("boundary after interior H=2", 4),
+                ("boundary after interior H=4 (previous default)", 4 | (4 << 8)), ("no overlap", 1),
+                ("3 streams, exchange skipped", 2), ("single launch, exchange skipped", 3)]
     for name, dbg in variants:
         os.environ["FDTD_B200_MGPU_DEBUG"] = str(dbg)
         best = None
