@@ -274,9 +274,22 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
     const int np = a.k_hi - a.k_lo, np2 = a.k_hi2 - a.k_lo2;
     int kc = fused_kc_override();
     if (kc <= 0) {
-        // 3 redundant plane iterations per chunk: keep chunks long, but leave enough CTAs for ~8 waves
-        kc = 128;
-        while (kc > 16 && (long long)gx * gy * ((np + np2 + kc - 1) / kc) < 148LL * MINB * 8) kc /= 2;
+        // Chunk count m of the (first) plane range: every chunk costs 3 redundant plane iterations plus ~2 of start-up,
+        // and the CTAs run in waves of one per SM, so minimise  waves(m) * (planes per chunk + 5)  -- long chunks, but
+        // a CTA count that fills its last wave (profiles/kc_sweep_r01.jsonl: 3 chunks of 171 beat 4 of 128 at 512^3).
+        const long long tiles = (long long)gx * gy, slots = 148LL * MINB;
+        long long best_cost = -1;
+        int best_m = 1;
+        for (int m = 1; m <= np; ++m) {
+            const int len = (np + m - 1) / m;
+            if (len > 512) continue;
+            if (len < 16 && m > 1) break;
+            const int m_eff = (np + len - 1) / len + (np2 > 0 ? (np2 + len - 1) / len : 0);
+            const long long waves = (tiles * m_eff + slots - 1) / slots;
+            const long long cost = waves * (len + 5);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_m = m; }
+        }
+        kc = (np + best_m - 1) / best_m;
     }
     if (kc > np) kc = np;
     a.kc = kc;
@@ -344,6 +357,7 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     a.src2 = src2; a.amp2 = amp2;
     a.use_tma = 1;
+    { const char* e = std::getenv("FDTD_B200_ST_CS"); a.st_cs = e ? std::atoi(e) : 1; }   // profiles/stcs_r01.jsonl: DRAM reads -3 %, +1.5 %
     const int by = variant < 3 ? by_of_variant[variant] : 16;
     for (int c = 0; c < 3 && a.use_tma; ++c)
         if (!encode_tmap(s, &a.tmE[c], EX + c, s->cur, by) || !encode_tmap(s, &a.tmB[c], BX + c, s->cur, by)) a.use_tma = 0;

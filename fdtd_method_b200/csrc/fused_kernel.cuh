@@ -78,6 +78,13 @@ __device__ __forceinline__ void stg_vec(T* p, const T (&o)[V]) {
     *reinterpret_cast<typename FusedVec<T>::type*>(p) = FusedVec<T>::pack(o);
 }
 
+// Streaming store (st.global.cs): the line is written once and not read again by this pass, so it should be the
+// first to leave L2 -- keeps the input lines that neighbouring tiles re-read (tile halos) resident longer.
+template <typename T, int V>
+__device__ __forceinline__ void stg_vec_cs(T* p, const T (&o)[V]) {
+    __stcs(reinterpret_cast<typename FusedVec<T>::type*>(p), FusedVec<T>::pack(o));
+}
+
 // Shared-memory row exchange: [buffer][component][warp row][lane] of 16-byte vectors.
 template <typename T, int BY>
 struct FusedSmem {

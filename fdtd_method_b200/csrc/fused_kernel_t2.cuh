@@ -71,6 +71,7 @@ struct FusedT2Args {
     // TMA: 3-D tensor maps {Ni, Nj, nk + 2*GHOST_PLANES} of the six input arrays, box = {32*V cells, BY rows, 1 plane};
     // tiles whose footprint needs no periodic wrap in i / j fill their ring slots with six tensor copies per plane
     int use_tma;
+    int st_cs;        // 1: output stores are streaming (evict-first in L2)
     alignas(64) CUtensorMap tmE[3];
     alignas(64) CUtensorMap tmB[3];
 };
@@ -378,12 +379,21 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
         if (ABL != 4) t2_update_E<T, V>(e1, b1, b2[0], b2[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
         if (c.out && stored && ABL != 2) {
             const long long o = (long long)kB * a.g.plane + c.roff;
-            stg_vec<T, V>(a.Eout[0] + o, e1[0]);
-            stg_vec<T, V>(a.Eout[1] + o, e1[1]);
-            stg_vec<T, V>(a.Eout[2] + o, e1[2]);
-            stg_vec<T, V>(a.Bout[0] + o, b1[0]);
-            stg_vec<T, V>(a.Bout[1] + o, b1[1]);
-            stg_vec<T, V>(a.Bout[2] + o, b1[2]);
+            if (a.st_cs) {
+                stg_vec_cs<T, V>(a.Eout[0] + o, e1[0]);
+                stg_vec_cs<T, V>(a.Eout[1] + o, e1[1]);
+                stg_vec_cs<T, V>(a.Eout[2] + o, e1[2]);
+                stg_vec_cs<T, V>(a.Bout[0] + o, b1[0]);
+                stg_vec_cs<T, V>(a.Bout[1] + o, b1[1]);
+                stg_vec_cs<T, V>(a.Bout[2] + o, b1[2]);
+            } else {
+                stg_vec<T, V>(a.Eout[0] + o, e1[0]);
+                stg_vec<T, V>(a.Eout[1] + o, e1[1]);
+                stg_vec<T, V>(a.Eout[2] + o, e1[2]);
+                stg_vec<T, V>(a.Bout[0] + o, b1[0]);
+                stg_vec<T, V>(a.Bout[1] + o, b1[1]);
+                stg_vec<T, V>(a.Bout[2] + o, b1[2]);
+            }
         }
     }
 }
