@@ -322,28 +322,39 @@ def run_ours(a):
         else:
             alg_bytes = cells_local * WORDS_PER_CELL_STEP * W
         fused = bool(info.fused)
+        pml = a.workload == "pml"
         t2_passes = g_passes_t2                       # two-step passes inside the timed region
-        t2 = fused and t2_passes * 2 >= a.steps - 1
-        # the dominant kernel: one launch = 2 Yee steps (T2 pass), 1 step (fused pass) or half a step (a sweep)
+        t2 = t2_passes * 2 >= a.steps - 1
+        # the dominant launch (group): one T2 launch = 2 Yee steps; one fused launch = 1 step; two sweeps = 1 step;
+        # PML solver: T2 launch on the main box's core + 4 rim sweeps = 2 steps, or 4 sweeps = 1 step
         steps_per_launch = 2 if t2 else 1
-        # average launch duration: CUDA events over the timed region on the solver's stream (launch gaps and the
-        # 3 us source kernels are < 1 % of it, profiles/launches_r01.csv)
+        # average duration: CUDA events over the timed region on the solver's stream (launch gaps and the 3 us
+        # source kernels are < 1 % of it, profiles/launches_r01.csv)
         kernel_ms = ms / (a.steps / steps_per_launch)
         achieved = alg_bytes * steps_per_launch / (kernel_ms * 1e-3) / 1e9
-        moved_words = 6 if t2 else (12 if fused else 18)
+        if pml:
+            main_words = 6 if t2 else 18
+            moved_bytes = ((cells_local - npml) * main_words + npml * WORDS_PER_PML_CELL_STEP) * W   # per step
+            kernel = ("PML step group: fused_BE_T2_kernel on the main box's core + 4 rim sweeps (sweep_B/E_kernel<PML>) = TWO Yee steps"
+                      if t2 else "PML step: sweep_B/E_kernel interior + shell launches (4 launches = one Yee step)")
+        else:
+            moved_words = 6 if t2 else (12 if fused else 18)
+            moved_bytes = cells_local * moved_words * W
+            kernel = ("fused_BE_T2_kernel (one launch = TWO Yee steps of this rank's slab)" if t2 else
+                      "fused_BE_kernel (one launch = one Yee step of this rank's slab)" if fused
+                      else "sweep_B_kernel + sweep_E_kernel (two launches = one Yee step)")
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(a.dtype, n) if a.workload == "periodic" else None,
+                "traffic": ncu_traffic(a.dtype, n) if not pml else None,
                 "peak_source": peak_src,
-                "kernel": ("fused_BE_T2_kernel (one launch = TWO Yee steps of this rank's slab)" if t2 else
-                           "fused_BE_kernel (one launch = one Yee step of this rank's slab)" if fused
-                           else "sweep_B_kernel + sweep_E_kernel (two launches = one Yee step)"),
+                "kernel": kernel,
                 "kernel_ms": kernel_ms, "steps_per_launch": steps_per_launch,
-                "algorithmic_bytes_per_cell_step": WORDS_PER_CELL_STEP * W,
-                "kernel_compulsory_bytes_per_cell_step": moved_words * W,
-                "kernel_compulsory_GBs": cells_local * moved_words * W * steps_per_launch / (kernel_ms * 1e-3) / 1e9,
-                "note": "achieved = SURVEY.md 8(d)'s 21 words per cell-step x cells x steps per launch / launch time; the temporally "
-                        "blocked pass really moves 6 words per cell-step (12 per launch), so frac > 1 is expected and "
-                        "kernel_compulsory_GBs / traffic give the physical DRAM view (DESIGN.md, 'Roofline accounting')"}
+                "algorithmic_bytes_per_cell_step": alg_bytes / cells_local,
+                "kernel_compulsory_bytes_per_cell_step": moved_bytes / cells_local,
+                "kernel_compulsory_GBs": moved_bytes * steps_per_launch / (kernel_ms * 1e-3) / 1e9,
+                "note": "achieved = SURVEY.md 8(d)'s algorithmic bytes (21 words per interior cell-step, 36 per PML cell-step) x cells x "
+                        "steps per launch / launch time; the temporally blocked pass really moves 6 words per cell-step (12 per "
+                        "launch), so frac > 1 is expected and kernel_compulsory_GBs / traffic give the physical DRAM view "
+                        "(DESIGN.md, 'Roofline accounting')"}
         line = {
             "metric": "Gcell-updates/s (E+B step)", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,

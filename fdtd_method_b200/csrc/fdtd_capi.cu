@@ -6,6 +6,7 @@
 //   fdtd_zeroed_currents FDTD::zeroed_currents             src/FDTD/FDTD.cpp:132-136
 //   fdtd_upload/download/scatter/gather  = reads and writes through `Field& get_field(Component)`, FDTD.cpp:138-151
 // There is no CPU implementation behind any of these: without a usable CUDA device they fail.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -101,7 +102,7 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
     a.n_half = n_half; a.do_pml = do_pml;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     a.mode = 0;
-    for (int d = 0; d < 3; ++d) { a.ib_lo[d] = 0; a.ib_hi[d] = 0; }
+    for (int d = 0; d < 3; ++d) { a.ib_lo[d] = 0; a.ib_hi[d] = 0; a.Bout[d] = a.f.B[d]; a.Eout[d] = a.f.E[d]; }
     dim3 block(SWEEP_BX, SWEEP_BY);
     const int gx = (s->g.Ni + SWEEP_BX * V - 1) / (SWEEP_BX * V);
     const int gy = (s->g.Nj + SWEEP_BY - 1) / SWEEP_BY;
@@ -134,6 +135,42 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
         const bool fringe = (a.ib_lo[0] != s->main_lo[0]) || (a.ib_hi[0] != s->main_hi[0]);
         if (is_B && !do_pml && !fringe) return FDTD_OK;   // deferred half step: nothing left outside the inner box
     }
+    if (is_B) sweep_B_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
+    else sweep_E_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
+    FDTD_CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    return FDTD_OK;
+}
+
+// Rim sweep of the PML solver's two-step pass: the PML = true kernel over every cell OUTSIDE the box ib (vector
+// granularity in i), reading generation `cur`; `to_new` = write the other generation instead of updating in place
+// (B sweep: B' -> gen cur^1; E sweep: reads B from gen cur^1, old E from gen cur, E' -> gen cur^1).
+template <typename T>
+static fdtd_status_t launch_rim_sweep(Solver* s, bool is_B, int n_half, const int ib_lo[3], const int ib_hi[3], bool to_new) {
+    constexpr int V = VecOf<T>::V;
+    SweepArgs<T> a;
+    a.g = s->g; a.c = s->c; a.p = make_pml(s); a.f = make_fields<T>(s); a.jbox = s->jbox;
+    a.k_lo = 0; a.k_hi = s->g.nk;
+    a.n_half = n_half; a.do_pml = 1;
+    a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
+    a.mode = 2;
+    for (int d = 0; d < 3; ++d) {
+        a.ib_lo[d] = ib_lo[d]; a.ib_hi[d] = ib_hi[d];
+        a.Bout[d] = a.f.B[d]; a.Eout[d] = a.f.E[d];
+    }
+    if (to_new) {
+        for (int d = 0; d < 3; ++d) {
+            T* nb = static_cast<T*>(s->p[BX + d][s->cur ^ 1]);
+            T* ne = static_cast<T*>(s->p[EX + d][s->cur ^ 1]);
+            if (is_B) a.Bout[d] = nb;
+            else { a.f.B[d] = nb; a.Eout[d] = ne; }
+        }
+    }
+    dim3 block(SWEEP_BX, SWEEP_BY);
+    const int gx = (s->g.Ni + SWEEP_BX * V - 1) / (SWEEP_BX * V);
+    const int gy = (s->g.Nj + SWEEP_BY - 1) / SWEEP_BY;
+    a.kc = pick_kc(s, gx * gy, s->g.nk);
+    dim3 grid(gx, gy, (s->g.nk + a.kc - 1) / a.kc);
     if (is_B) sweep_B_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
     else sweep_E_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
     FDTD_CUDA_TRY(cudaGetLastError());
@@ -277,7 +314,9 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
         // Chunk count m of the (first) plane range: every chunk costs 3 redundant plane iterations plus ~2 of start-up,
         // and the CTAs run in waves of one per SM, so minimise  waves(m) * (planes per chunk + 5)  -- long chunks, but
         // a CTA count that fills its last wave (profiles/kc_sweep_r01.jsonl: 3 chunks of 171 beat 4 of 128 at 512^3).
-        const long long tiles = (long long)gx * gy, slots = 148LL * MINB;
+        // (CTAs whose output tile misses the store box exit at once: count the ones that work)
+        const long long tiles = (long long)std::min(gx, (a.sb_hi[0] - a.sb_lo[0] + TIU - 1) / TIU + 1) *
+                                std::min(gy, (a.sb_hi[1] - a.sb_lo[1] + TJU - 1) / TJU + 1), slots = 148LL * MINB;
         long long best_cost = -1;
         int best_m = 1;
         for (int m = 1; m <= np; ++m) {
@@ -356,6 +395,10 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
     a.k_lo = k_lo; a.k_hi = k_hi; a.k_lo2 = k_lo2; a.k_hi2 = k_hi2; a.n_half = n_half;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     a.src2 = src2; a.amp2 = amp2;
+    for (int d = 0; d < 2; ++d) {
+        a.sb_lo[d] = s->pml_t2 ? s->sb_lo[d] : 0;
+        a.sb_hi[d] = s->pml_t2 ? s->sb_hi[d] : (d == 0 ? s->g.Ni : s->g.Nj);
+    }
     a.use_tma = 1;
     { const char* e = std::getenv("FDTD_B200_ST_CS"); a.st_cs = e ? std::atoi(e) : 1; }   // profiles/stcs_r01.jsonl: DRAM reads -3 %, +1.5 %
     const int by = variant < 3 ? by_of_variant[variant] : 16;
@@ -473,6 +516,21 @@ static fdtd_status_t exchange_t2(Solver* s, cudaStream_t stream) {
     fdtd_status_t st = nccl_exchange(s, x, n, stream);
     if (st == FDTD_OK) { s->ghosts_t2_valid = true; s->ghosts_fused_valid = true; s->ghosts_e_valid = true; s->ghosts_b_valid = true; }
     return st;
+}
+
+// Mid-pass exchanges of the PML solver's two-step pass on slab ranks: (Bx, By) top plane of generation `gen` -> upper
+// neighbour's plane -1, or (Ex, Ey) bottom plane -> lower neighbour's plane nk (only the rim cells of those planes
+// are meaningful on both sides, and only those are read).
+static fdtd_status_t exchange_pair_planes(Solver* s, bool b_to_upper, int gen) {
+    if (s->cfg.nranks <= 1) return FDTD_OK;
+    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
+    const size_t bytes = (size_t)s->g.plane * s->esz;
+    PlaneXfer x[2];
+    for (int c = 0; c < 2; ++c) {
+        if (b_to_upper) x[c] = PlaneXfer{plane_ptr(s, BX + c, gen, s->g.nk - 1), up, plane_ptr(s, BX + c, gen, -1), down, bytes};
+        else x[c] = PlaneXfer{plane_ptr(s, EX + c, gen, 0), down, plane_ptr(s, EX + c, gen, s->g.nk), up, bytes};
+    }
+    return nccl_exchange(s, x, 2, s->stream);
 }
 
 static void invalidate_ghosts(Solver* s) {
@@ -602,6 +660,60 @@ static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, LaunchFn launch, E
     return launch(0, s->g.nk, 0, 0);
 }
 
+// PML solver, two steps in one pass.  Reach of the T2 pass is 2 cells, so it is exact on the store box
+// SB = main box shrunk by 2 (on the axes that have a shell; i bounds aligned to the vector width) as long as it reads
+// generation `cur` untouched.  Everything outside SB -- the shell and a thin rim of main cells -- is advanced by the
+// sweep kernels, with the reference's per-cell arithmetic (FDTD_PML.cpp:343-365), on shrinking regions:
+//     T2 pass                 gen cur -> gen new on SB                       (S0 -> S2)
+//     B sweep, in place       outside SB shrunk by 2 (2V in i)               (B1 needs E0 at +1: any cell)
+//     E sweep, in place       outside SB shrunk by 1 (V in i)                (E1 needs B1 at -1: covered by the line above)
+//     [device source: J of the second step]
+//     B sweep, cur -> new     outside SB                                     (B2 needs E1 at +1: covered)
+//     E sweep, cur -> new     outside SB, B read from gen new                (E2 needs B2 at -1: rim or SB, both in gen new)
+// Every cell ends up in gen new; the split fields are only touched by the sweeps, twice, in place.
+static void shrink_box(const Solver* s, int by, int by_i, int lo[3], int hi[3]) {
+    for (int a = 0; a < 3; ++a) {
+        const int d = (s->pml[a] > 0) ? (a == 0 ? by_i : by) : 0;   // no shell on this axis: the box spans the periodic axis
+        lo[a] = s->sb_lo[a] + d;
+        hi[a] = s->sb_hi[a] - d;
+    }
+}
+
+static fdtd_status_t advance_pml_pair(Solver* s, int n_half, int src2, double amp2) {
+    const int V = (int)(16 / s->esz);
+    fdtd_status_t st;
+    // local planes of the store box on this rank (possibly none: a rank inside the k shell only runs rim sweeps)
+    const int klo = std::max(s->sb_lo[2] - s->g.k0, 0), khi = std::min(s->sb_hi[2] - s->g.k0, s->g.nk);
+    auto t2_clipped = [&](int lo, int hi, int lo2, int hi2) -> fdtd_status_t {
+        lo = std::max(lo, klo); hi = std::min(hi, khi);
+        lo2 = std::max(lo2, klo); hi2 = std::min(hi2, khi);
+        if (hi <= lo) { lo = lo2; hi = hi2; lo2 = hi2 = 0; }
+        if (hi2 <= lo2) lo2 = hi2 = 0;
+        if (hi <= lo) return FDTD_OK;
+        return DISPATCH(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2);
+    };
+    // slab ranks: ring exchange of the two ghost planes per side (+ J) overlapped with the interior planes, as in the
+    // periodic solver; single GPU: one launch
+    st = overlapped(s, s->ghosts_t2_valid, t2_clipped, [&](cudaStream_t q) { return exchange_t2(s, q); });
+    if (st != FDTD_OK) return st;
+    int lo[3], hi[3];
+    shrink_box(s, 2, 2 * V, lo, hi);
+    if ((st = DISPATCH(s, launch_rim_sweep, s, true, n_half, lo, hi, false)) != FDTD_OK) return st;
+    if ((st = exchange_pair_planes(s, true, s->cur)) != FDTD_OK) return st;          // B1 top plane -> upper rank's plane -1
+    shrink_box(s, 1, V, lo, hi);
+    if ((st = DISPATCH(s, launch_rim_sweep, s, false, 0, lo, hi, false)) != FDTD_OK) return st;
+    if ((st = exchange_pair_planes(s, false, s->cur)) != FDTD_OK) return st;         // E1 bottom plane -> lower rank's plane nk
+    if (src2) {
+        // the rim may meet the source box: the second step's sweeps read J from the arrays
+        if ((st = DISPATCH(s, launch_source, s, amp2, 0)) != FDTD_OK) return st;
+    }
+    shrink_box(s, 0, 0, lo, hi);
+    if ((st = DISPATCH(s, launch_rim_sweep, s, true, 2, lo, hi, true)) != FDTD_OK) return st;
+    if ((st = exchange_pair_planes(s, true, s->cur ^ 1)) != FDTD_OK) return st;      // B2 top plane (new generation)
+    if ((st = DISPATCH(s, launch_rim_sweep, s, false, 0, lo, hi, true)) != FDTD_OK) return st;
+    return FDTD_OK;
+}
+
 // Advance by one step, or by two when the temporally blocked pass applies; *done = steps advanced.
 static fdtd_status_t advance(Solver* s, int remaining, int* done) {
     fdtd_status_t st;
@@ -622,7 +734,17 @@ static fdtd_status_t advance(Solver* s, int remaining, int* done) {
         }
     }
     const int n_half = s->b_pending ? 2 : 1;
-    if (s->fused) {
+    if (s->pml_t2 && remaining >= 2 && !t2_disabled_by_env() &&
+        !(s->src_active && s->src_t >= (int)s->src_amp.size())) {   // (the source does not retire between the two steps)
+        const int src2 = s->src_active ? 1 : 0;
+        const double amp2 = src2 ? s->src_amp[s->src_t] : 0.0;
+        st = advance_pml_pair(s, n_half, src2, amp2);
+        if (st != FDTD_OK) return st;
+        if (src2) { s->src_t++; s->j_stale = false; }   // advance_pml_pair has written the second step's J
+        s->passes_t2++;
+        *done = 2;
+        s->cur ^= 1;
+    } else if (s->fused) {
         // Pair this step with the next one unless the source retires in between (J would have to change to zero).
         const bool src_ends = s->src_active && s->src_t >= (int)s->src_amp.size();
         if (s->t2 && remaining >= 2 && !src_ends && !t2_disabled_by_env()) {
@@ -785,10 +907,28 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
     const int V = (int)(16 / s->esz);
     s->fused = !s->has_pml && !(cfg->flags & FDTD_FLAG_NO_FUSION) && (P.Ni % V == 0);
     s->t2 = s->fused && !(cfg->flags & FDTD_FLAG_NO_TEMPORAL) && s->g.nk >= 4;
+    // fp64 by default: the fp32 T2 pass is conversion-bound and loses to the two lean interior sweeps
+    // (measured 5.5 vs 4.8 ms per step at 512^3); FDTD_B200_PML_T2_F32=1 turns it on anyway (parity tests do).
+    const char* f32_pair = std::getenv("FDTD_B200_PML_T2_F32");
+    const bool pair_dtype_ok = (s->esz == 8) || (f32_pair && std::atoi(f32_pair) != 0);
+    if (s->has_pml && pair_dtype_ok && !(cfg->flags & (FDTD_FLAG_NO_FUSION | FDTD_FLAG_NO_TEMPORAL)) && (P.Ni % V == 0) && P.Nk / cfg->nranks >= 4) {
+        // store box of the two-step pass: main box shrunk by the pass's reach on the axes that have a shell
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) {
+            const int d = s->pml[a] > 0 ? 2 : 0;
+            s->sb_lo[a] = s->main_lo[a] + d;
+            s->sb_hi[a] = s->main_hi[a] - d;
+        }
+        s->sb_lo[0] = (s->sb_lo[0] + V - 1) / V * V;
+        s->sb_hi[0] = s->sb_hi[0] / V * V;
+        // worth it only when the core is a real volume (and the rim boxes below stay non-degenerate)
+        ok = (s->sb_hi[0] - s->sb_lo[0] >= 8 * V) && (s->sb_hi[1] - s->sb_lo[1] >= 8) && (s->sb_hi[2] - s->sb_lo[2] >= 8);
+        s->pml_t2 = ok;
+    }
 
     for (int c = 0; c < NCOMP && st == FDTD_OK; ++c) {
         st = alloc_array(s, &s->base[c][0], &s->p[c][0]);
-        if (st == FDTD_OK && s->fused && c < JX) st = alloc_array(s, &s->base[c][1], &s->p[c][1]);
+        if (st == FDTD_OK && (s->fused || s->pml_t2) && c < JX) st = alloc_array(s, &s->base[c][1], &s->p[c][1]);
     }
     if (st != FDTD_OK) return bail(st);
     if (s->has_pml) {
@@ -1166,7 +1306,7 @@ fdtd_status_t fdtd_get_info(fdtd_solver_t* h, fdtd_info_t* info) {
     info->steps_done = s->steps_done;
     info->fused = s->fused ? 1 : 0;
     info->rank = s->cfg.rank; info->nranks = s->cfg.nranks; info->device = s->device;
-    info->temporal = s->t2 ? 1 : 0;
+    info->temporal = (s->t2 || s->pml_t2) ? 1 : 0;
     info->passes_t2 = s->passes_t2;
     return FDTD_OK;
 }

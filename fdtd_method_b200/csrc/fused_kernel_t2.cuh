@@ -72,6 +72,10 @@ struct FusedT2Args {
     // tiles whose footprint needs no periodic wrap in i / j fill their ring slots with six tensor copies per plane
     int use_tma;
     int st_cs;        // 1: output stores are streaming (evict-first in L2)
+    // Store box in i, j (global coordinates, i bounds multiples of V): only cells inside it are written, CTAs whose
+    // output tile misses it exit at once.  The whole grid for the periodic solver; the main box shrunk by the pass's
+    // dependency reach (2 cells) for the PML solver, whose shell and rim are advanced by the sweep kernels.
+    int sb_lo[2], sb_hi[2];
     alignas(64) CUtensorMap tmE[3];
     alignas(64) CUtensorMap tmB[3];
 };
@@ -428,7 +432,8 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     c.needE2 = c.needB2 && (ty >= 2) && (j < Nj);
     c.ldE = lane_active && row_active;
     c.producer = TMA && (ty == BY - 1) && (tx == 0);   // the top halo row's warp has no arithmetic of its own
-    c.out = c.needE2 && lane_active && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (c.i < Ni);
+    c.out = c.needE2 && lane_active && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (c.i < Ni) &&
+            (c.i >= a.sb_lo[0]) && (c.i + V <= a.sb_hi[0]) && (j >= a.sb_lo[1]) && (j < a.sb_hi[1]);
     c.roff = (long long)c.jw * a.g.pitch + (lane_active ? iw : 0);
     {
         const bool second = (int)blockIdx.z >= a.nz1;
@@ -501,6 +506,8 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     // CTA-uniform: only the few tiles whose footprint (halo included) meets the box where J may be non-zero run
     // the loop that knows about currents; tiles that need no periodic wrap in i / j load through TMA.
     const int i0 = blockIdx.x * (FUSED_OUT_LANES * V) - V, j0 = blockIdx.y * (BY - 4) - 2;
+    // output tile = [i0 + V, i0 + V + 30 V) x [j0 + 2, j0 + BY - 2)
+    if (i0 + V >= a.sb_hi[0] || i0 + V + FUSED_OUT_LANES * V <= a.sb_lo[0] || j0 + 2 >= a.sb_hi[1] || j0 + BY - 2 <= a.sb_lo[1]) return;
     const bool second = (int)blockIdx.z >= a.nz1;
     const int kb = (second ? a.k_lo2 : a.k_lo) + ((int)blockIdx.z - (second ? a.nz1 : 0)) * a.kc;
     const int k0 = a.g.k0 + kb - 2, k1 = a.g.k0 + min(kb + a.kc, second ? a.k_hi2 : a.k_hi) + 1;

@@ -35,6 +35,10 @@ struct Solver {
     int cur = 0;
     bool fused = false;
     bool t2 = false;               // fdtd_step(n >= 2) pairs steps into the temporally blocked T2 pass
+    // PML solver, two steps per pass: the T2 pass advances the store box sb (main box shrunk by 2 on the axes that have
+    // a shell), the sweep kernels advance everything outside it twice (csrc/fdtd_capi.cu::advance_pml_pair)
+    bool pml_t2 = false;
+    int sb_lo[3] = {0, 0, 0}, sb_hi[3] = {0, 0, 0};
     bool j_stale = false;          // a T2 pass evaluated the device source in-kernel: the J arrays lag one step
     int64_t device_bytes = 0;
 

@@ -45,6 +45,10 @@ struct SweepArgs {
     // i bounds aligned inward to the vector width), mode 2 = only cells outside it, mode 0 = every cell.
     int mode;
     int ib_lo[3], ib_hi[3];   // inner box, GLOBAL coordinates
+    // Where the sweep writes: f.B / f.E themselves (in place, the default) or the other generation (the second
+    // step of the PML solver's two-step pass, whose core cells the T2 pass has already written there).
+    T* Bout[3];
+    T* Eout[3];
 };
 
 constexpr int SWEEP_BX = 32;  // lanes along i
@@ -76,9 +80,12 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
     const T* __restrict__ Ex = a.f.E[0];
     const T* __restrict__ Ey = a.f.E[1];
     const T* __restrict__ Ez = a.f.E[2];
-    T* __restrict__ Bx = a.f.B[0];
-    T* __restrict__ By = a.f.B[1];
-    T* __restrict__ Bz = a.f.B[2];
+    const T* Bx = a.f.B[0];   // (no __restrict__: Bout aliases f.B when the sweep is in place)
+    const T* By = a.f.B[1];
+    const T* Bz = a.f.B[2];
+    T* BxO = a.Bout[0];
+    T* ByO = a.Bout[1];
+    T* BzO = a.Bout[2];
     const double cx = a.c.cBx, cy = a.c.cBy, cz = a.c.cBz;
 
     bool col_main[V];
@@ -208,9 +215,9 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
                 bz[e] = round_store<T>(dadd(szx[e], szy[e]));
             }
         }
-        stv(Bx + o, bx, nvalid);
-        stv(By + o, by, nvalid);
-        stv(Bz + o, bz, nvalid);
+        stv(BxO + o, bx, nvalid);
+        stv(ByO + o, by, nvalid);
+        stv(BzO + o, bz, nvalid);
         if (PML && any_pml) {
             stv(a.f.SB[S_XY] + o, sxy, nvalid); stv(a.f.SB[S_XZ] + o, sxz, nvalid);
             stv(a.f.SB[S_YX] + o, syx, nvalid); stv(a.f.SB[S_YZ] + o, syz, nvalid);
@@ -244,9 +251,12 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
     const long long row = (long long)j * a.g.pitch;
     const long long rowp = (long long)jp * a.g.pitch;
 
-    T* __restrict__ Ex = a.f.E[0];
-    T* __restrict__ Ey = a.f.E[1];
-    T* __restrict__ Ez = a.f.E[2];
+    const T* Ex = a.f.E[0];   // (no __restrict__: Eout aliases f.E when the sweep is in place)
+    const T* Ey = a.f.E[1];
+    const T* Ez = a.f.E[2];
+    T* ExO = a.Eout[0];
+    T* EyO = a.Eout[1];
+    T* EzO = a.Eout[2];
     const T* __restrict__ Bx = a.f.B[0];
     const T* __restrict__ By = a.f.B[1];
     const T* __restrict__ Bz = a.f.B[2];
@@ -383,9 +393,9 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
                 e_z[e] = dadd(szy[e], szx[e]);
             }
         }
-        stv(Ex + o, e_x, nvalid);
-        stv(Ey + o, e_y, nvalid);
-        stv(Ez + o, e_z, nvalid);
+        stv(ExO + o, e_x, nvalid);
+        stv(EyO + o, e_y, nvalid);
+        stv(EzO + o, e_z, nvalid);
         if (PML && any_pml) {
             stv(a.f.SE[S_XY] + o, sxy, nvalid); stv(a.f.SE[S_XZ] + o, sxz, nvalid);
             stv(a.f.SE[S_YX] + o, syx, nvalid); stv(a.f.SE[S_YZ] + o, syz, nvalid);

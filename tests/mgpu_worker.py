@@ -34,6 +34,9 @@ def main():
         ((64, 48, 40 * world), 0.1, False, np.float64, 5),     # PML interior/shell split on slabs
         ((32, 16, 8 * world), None, True, np.float64, 6),      # smallest slab that takes the overlapped path (H = 2)
         ((64, 24, 12 * world), None, True, np.float32, 5),     # overlapped path, fp32
+        ((64, 48, 24 * world), 0.1, True, np.float64, 6),      # PML two-step pass on slabs: T2 core + rim sweeps + mid-pass exchanges
+        ((64, 40, 20 * world), 0.2, True, np.float64, 5),      # ... k shell takes a large part of the first / last slab
+        ((64, 9, 16 * world), 0.07, True, np.float64, 5),      # ... no shell in j, thin shells elsewhere
     ]
     failures = 0
     for shape, pml, fusion, dtype, steps in cases:

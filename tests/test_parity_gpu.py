@@ -133,6 +133,64 @@ def test_pml_interior_shell_split(shape, pml, dtype, pml_split):
     assert_bit_equal(o, g, what=f"pml split={pml_split} {shape}")
 
 
+@pytest.mark.parametrize("shape,pml,dtype", [((64, 48, 48), 0.1, np.float64), ((50, 44, 44), 0.1, np.float64),
+                                             ((52, 44, 44), 0.1, np.float32), ((64, 9, 48), 0.1, np.float64),
+                                             ((64, 40, 72), 0.07, np.float64), ((128, 64, 40), 0.2, np.float64),
+                                             ((32, 64, 9), 0.1, np.float64)])
+def test_pml_two_step_pass(shape, pml, dtype, monkeypatch):
+    """fdtd_step(n >= 2) on a PML solver: T2 pass on the main box's core + rim sweeps for the shell and the band
+    around it (two steps per pass) must equal n x update_fields() of the oracle bit for bit -- distinct Jx/Jy/Jz
+    everywhere (so the rim reads J), thickness 0 on an axis (periodic there), fp32, odd step counts, reads in between."""
+    Ni, Nj, Nk = shape
+    monkeypatch.setenv("FDTD_B200_PML_T2_F32", "1")   # the fp32 pair path is off by default (slower than the sweeps)
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), pml=pml, dtype=dtype)
+    assert g.info().temporal == 1 and g.info().fused == 0
+    load_both(o, g, seeded_fields(91, (Nk, Nj, Ni), dtype=dtype, same_j=False))
+    o.step(7)
+    g.step(7)
+    assert g.info().passes_t2 == 3
+    assert_bit_equal(o, g, what=f"pml T2 {shape} after step(7)")
+    o.update_fields(); g.update_fields()
+    o.step(4); g.step(4)
+    assert g.info().passes_t2 == 5
+    assert_bit_equal(o, g, what=f"pml T2 {shape} after update_fields + step(4)")
+    # the same solver without the two-step pass gives the same bits
+    _, h = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), pml=pml, dtype=dtype, temporal=False)
+    f = seeded_fields(91, (Nk, Nj, Ni), dtype=dtype, same_j=False)
+    for c in range(9):
+        h.upload(c, f[c])
+    h.step(12)
+    assert h.info().passes_t2 == 0
+    for c in range(6):
+        assert np.array_equal(h.download(c), g.download(c))
+
+
+def test_pml_two_step_pass_device_source_across_shell_rim_core():
+    """Device-resident source whose box straddles shell, rim and core cells, retiring in the middle of the run:
+    the core takes the second step's J in the T2 kernel, the rim sweeps from the J arrays."""
+    import math
+    n, pml, steps, active = 48, 0.15, 11, 5
+    o, g = make_pair(n, n, n, pml=pml)
+    assert g.info().temporal == 1
+    load_both(o, g, seeded_fields(17, (n, n, n)), comps=range(6))
+    lo, hi = (4, 8, 9), (14, 12, 13)          # shell thickness 7: i = 4..6 shell, 7..9 rim, 10.. core
+    w = [[0.3 + 0.1 * math.cos(0.7 * i) for i in range(lo[a], hi[a])] for a in range(3)]
+    amp = [math.sin(0.4 * (t + 1)) for t in range(active)]
+    g.set_source(lo, hi, w[0], w[1], w[2], amp)
+    g.step(steps)
+    for t in range(steps):
+        for c in (6, 7, 8):
+            j = o.field(c)
+            j[...] = 0.0
+            if t < active:
+                for k in range(lo[2], hi[2]):
+                    for jj in range(lo[1], hi[1]):
+                        for i in range(lo[0], hi[0]):
+                            j[k, jj, i] = ((amp[t] * w[0][i - lo[0]]) * w[1][jj - lo[1]]) * w[2][k - lo[2]]
+        o.update_fields()
+    assert_bit_equal(o, g, what="pml T2 device source")
+
+
 def test_pml_explicit_thickness_matches_percent():
     Ni, Nj, Nk = 20, 20, 20
     o, g = make_pair(Ni, Nj, Nk, pml=0.2, pml_thickness=(4, 4, 4))
