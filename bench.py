@@ -188,9 +188,10 @@ def run_reference_arm(a):
 
 
 def workload_config(a, world, note=None):
-    cfg = {"workload": f"{a.n}^3 {a.dtype} Yee grid per GPU, {'periodic' if a.workload == 'periodic' else 'PML 32 cells (pml_percent 0.0625 in i/j, explicit thickness)'}"
+    strong = getattr(a, "scaling", "weak") == "strong"
+    cfg = {"workload": f"{a.n}^3 {a.dtype} Yee grid {'in total (z-slabs of n/N planes, BASELINE configs[3])' if strong else 'per GPU'}, {'periodic' if a.workload == 'periodic' else 'PML 32 cells (pml_percent 0.0625 in i/j, explicit thickness)'}"
                        f", random E/B seed 42 + sample.cpp point current source active every step (BASELINE configs[2])",
-           "grid": [a.n, a.n, a.n * world], "decomposition": f"z-slab x{world}" if world > 1 else "single GPU",
+           "grid": [a.n, a.n, a.n * world if getattr(a, "scaling", "weak") == "weak" else a.n], "decomposition": f"z-slab x{world}" if world > 1 else "single GPU",
            "dx=dy=dz": "C", "dt": 0.2, "l2": "working set 12+ GiB per GPU >> 126 MB L2 (no flush needed)"}
     if note:
         cfg["note"] = note
@@ -217,7 +218,7 @@ def run_ours(a):
     n = a.n
     dtype = np.float64 if a.dtype == "f64" else np.float32
     W = 8 if a.dtype == "f64" else 4
-    Nk = n * world
+    Nk = n * world if a.scaling == "weak" else n
     p = fb.Parameters(n, n, Nk, -n / 2 * C, n / 2 * C, -n / 2 * C, n / 2 * C, -Nk / 2 * C, Nk / 2 * C, C, C, C)
     kw = dict(dtype=dtype, device=local, rank=rank, nranks=world)
     if a.workload == "pml":
@@ -286,16 +287,16 @@ def run_ours(a):
     e2e_steps = a.steps
     barrier()
     t0 = time.perf_counter()
-    for c in range(6):
+    for c in range(0 if a.no_e2e else 6):
         g.upload(c, host[c].numpy())
     probe_sum = 0.0
-    for t in range(e2e_steps):
+    for t in range(0 if a.no_e2e else e2e_steps):
         vals = (((amp[t] * wprod[:, 0]) * wprod[:, 1]) * wprod[:, 2]).astype(dtype)
         for c in (6, 7, 8):
             g.scatter(c, src_idx, vals)
         g.update_fields()
         probe_sum += float(g.gather(0, probe_idx).sum())
-    for c in range(6):
+    for c in range(0 if a.no_e2e else 6):
         g.download(c, host[c].numpy())
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -312,7 +313,7 @@ def run_ours(a):
         dist.all_reduce(ll, op=dist.ReduceOp.SUM)
         launches = int(ll[0])
     value = cells_total * a.steps / (ms * 1e-3) / 1e9
-    e2e_value = cells_total * e2e_steps / e2e_s / 1e9
+    e2e_value = None if a.no_e2e else cells_total * e2e_steps / e2e_s / 1e9
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -358,7 +359,7 @@ def run_ours(a):
         line = {
             "metric": "Gcell-updates/s (E+B step)", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "scaling": a.scaling, "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": workload_config(a, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -400,10 +401,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=512)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--workload", default="periodic", choices=["periodic", "pml"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): n^3 per GPU; strong: n^3 in total, z-slabs of n/N planes (BASELINE configs[3])")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (scaling probes)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3

@@ -72,7 +72,7 @@ typedef enum fdtd_status {
 #define FDTD_FLAG_J_OPENMP_QUIRK 0x1u /* Jx feeds Ex, Ey AND Ez like FDTD_openmp (FDTD.cpp:85,88,91).
                                          Default is the FDTD_kokkos behaviour (kokkos_functors.h:81-89). */
 #define FDTD_FLAG_NO_FUSION 0x2u      /* force the two-sweep kernels (B sweep, E sweep) instead of the fused pass */
-#define FDTD_FLAG_NO_GRAPH 0x4u       /* never capture fdtd_step(n) into a CUDA graph */
+#define FDTD_FLAG_NO_GRAPH 0x4u       /* reserved, ignored: fdtd_step(n) issues one pass launch per two steps and is not graph-captured */
 #define FDTD_FLAG_NO_OVERLAP 0x8u     /* multi-GPU: issue the halo exchange on the compute stream (no overlap) */
 #define FDTD_FLAG_NO_PML_SPLIT 0x10u  /* PML: one launch per sweep with a per-cell predicate instead of interior + shell launches */
 #define FDTD_FLAG_NO_TEMPORAL 0x20u   /* fdtd_step(n): never pair steps into the temporally blocked two-step pass */
