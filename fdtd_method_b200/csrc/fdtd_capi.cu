@@ -253,7 +253,7 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     cudaError_t e;
     int variant = fused_variant();
-    if (variant < 0) variant = (sizeof(T) == 8) ? 5 : 0;   // measured best on B200 (profiles/sweep_r01.md)
+    if (variant < 0) variant = (sizeof(T) == 8) ? 28 : 0;  // measured best on B200 (profiles/sweep_t2_r01.md, profiles/t1_variants_r01.jsonl: v28 2.34 ms, v5 2.42 ms)
     switch (variant) {
         default:
         case 0: e = launch_fused_variant<T, 8, 1, 2>(s, a); break;
@@ -319,9 +319,15 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
                                 std::min(gy, (a.sb_hi[1] - a.sb_lo[1] + TJU - 1) / TJU + 1), slots = 148LL * MINB;
         long long best_cost = -1;
         int best_m = 1;
+        // Second constraint: CTAs are dispatched in id order as SMs free up, so the start-time skew between a tile and
+        // its y-neighbour (gx ids away) is about (chunk duration) x gx / (CTAs in flight); once it exceeds the time a
+        // line survives in L2, the 4 halo rows of every 16-row tile are read from DRAM twice.  Measured
+        // (profiles/kc_traffic_r01.jsonl): fine up to len * gx ~ 1540 (512^3, 171 planes: 1.09x compulsory traffic),
+        // 1.23x at 2300, 1.37x at 9200 (1024^3 with 512-plane chunks: 87 instead of 110 Gcell/s).
+        const int len_cap = std::max(32, 1600 / std::max(gx, 1));
         for (int m = 1; m <= np; ++m) {
             const int len = (np + m - 1) / m;
-            if (len > 512) continue;
+            if (len > len_cap && len > 32) continue;
             if (len < 16 && m > 1) break;
             const int m_eff = (np + len - 1) / len + (np2 > 0 ? (np2 + len - 1) / len : 0);
             const long long waves = (tiles * m_eff + slots - 1) / slots;
@@ -334,8 +340,15 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
     a.kc = kc;
     a.nz1 = (np + kc - 1) / kc;
     const int gz = a.nz1 + (np2 + kc - 1) / kc;
-    if (a.n_half == 2) fused_BE_T2_kernel<T, BY, MINB, true, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
-    else fused_BE_T2_kernel<T, BY, MINB, false, ABL><<<dim3(gx, gy, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
+    a.gx = gx; a.gy = gy;
+    {
+        const char* e = std::getenv("FDTD_B200_T2_STRIP");   // tile columns per strip; >= gx = row-major ids
+        int w = e ? std::atoi(e) : gx;   // row-major: measured best (profiles/strip_r01.jsonl) -- a missed x-neighbour costs
+                                          // as much as a missed y-neighbour (whole 128-byte lines at both ends of a 512-byte row)
+        a.strip_w = w < 1 ? 1 : (w > gx ? gx : w);
+    }
+    if (a.n_half == 2) fused_BE_T2_kernel<T, BY, MINB, true, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
+    else fused_BE_T2_kernel<T, BY, MINB, false, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -958,6 +971,37 @@ static fdtd_status_t check_handle(fdtd_solver_t* h, Solver** s) {
     return FDTD_OK;
 }
 
+static fdtd_status_t run_steps(Solver* s, int nsteps) {
+    fdtd_status_t st = FDTD_OK;
+    for (int t = 0; t < nsteps;) {
+        int done = 1;
+        st = advance(s, nsteps - t, &done);
+        if (st != FDTD_OK) return st;
+        t += done;
+    }
+    return materialize_J(s);
+}
+
+// Run the update_fields() call that fdtd_update_fields() recorded but did not issue (see Solver::lazy_steps).
+static fdtd_status_t flush_lazy(Solver* s) {
+    if (!s->lazy_steps) return FDTD_OK;
+    const int n = s->lazy_steps;
+    s->lazy_steps = 0;
+    return run_steps(s, n);
+}
+
+// Entry of every call that reads or changes solver state: the handle, then the recorded step.
+static fdtd_status_t enter(fdtd_solver_t* h, Solver** s) {
+    fdtd_status_t st = check_handle(h, s);
+    if (st != FDTD_OK) return st;
+    return flush_lazy(*s);
+}
+
+static bool lazy_disabled_by_env() {
+    const char* e = std::getenv("FDTD_B200_NO_LAZY");
+    return e && std::atoi(e) != 0;
+}
+
 static fdtd_status_t check_component(int comp) {
     if (comp < EX || comp > JZ) return fail(FDTD_ERR_INVALID_COMPONENT, "ERROR: Invalid field component");   // FDTD.cpp:149
     return FDTD_OK;
@@ -1115,20 +1159,34 @@ fdtd_status_t fdtd_step(fdtd_solver_t* h, int nsteps) {
     fdtd_status_t st = check_handle(h, &s);
     if (st != FDTD_OK) return st;
     if (nsteps < 0) return fail(FDTD_ERR_BAD_ARGUMENT, "negative step count");
-    for (int t = 0; t < nsteps;) {
-        int done = 1;
-        st = advance(s, nsteps - t, &done);
-        if (st != FDTD_OK) return st;
-        t += done;
-    }
-    return materialize_J(s);
+    const int n = nsteps + s->lazy_steps;   // a recorded update_fields() call joins the batch
+    s->lazy_steps = 0;
+    return run_steps(s, n);
 }
 
-fdtd_status_t fdtd_update_fields(fdtd_solver_t* h) { return fdtd_step(h, 1); }
+// FDTD::update_fields().  The reference's callers step one call at a time (sample.cpp:57-87, test_FDTD_method.cpp:32-41);
+// so that such loops still reach the two-step pass, an odd call is recorded and returns at once, and the next call
+// issues both steps as one pass.  Anything that reads or changes state (field access, J writes, sources, sync, timers)
+// runs the recorded step first, so the observable sequence is exactly one step per call (errors of a deferred step
+// surface at that later call).  FDTD_B200_NO_LAZY=1 issues every call immediately.
+fdtd_status_t fdtd_update_fields(fdtd_solver_t* h) {
+    Solver* s;
+    fdtd_status_t st = check_handle(h, &s);
+    if (st != FDTD_OK) return st;
+    if (s->lazy_steps) {
+        s->lazy_steps = 0;
+        return run_steps(s, 2);
+    }
+    if ((s->t2 || s->pml_t2) && !t2_disabled_by_env() && !lazy_disabled_by_env()) {
+        s->lazy_steps = 1;
+        return FDTD_OK;
+    }
+    return run_steps(s, 1);
+}
 
 fdtd_status_t fdtd_zeroed_currents(fdtd_solver_t* h) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     s->src_active = false;
     return zero_currents_impl(s);
@@ -1136,7 +1194,7 @@ fdtd_status_t fdtd_zeroed_currents(fdtd_solver_t* h) {
 
 fdtd_status_t fdtd_upload(fdtd_solver_t* h, int comp, const void* host, size_t count) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     if ((st = check_component(comp)) != FDTD_OK) return st;
     const size_t expect = (size_t)s->g.Ni * s->g.Nj * s->g.nk;
@@ -1158,7 +1216,7 @@ fdtd_status_t fdtd_upload(fdtd_solver_t* h, int comp, const void* host, size_t c
 
 fdtd_status_t fdtd_download(fdtd_solver_t* h, int comp, void* host, size_t count) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     if ((st = check_component(comp)) != FDTD_OK) return st;
     const size_t expect = (size_t)s->g.Ni * s->g.Nj * s->g.nk;
@@ -1176,7 +1234,7 @@ fdtd_status_t fdtd_download(fdtd_solver_t* h, int comp, void* host, size_t count
 
 fdtd_status_t fdtd_scatter(fdtd_solver_t* h, int comp, const int64_t* idx, const void* values, size_t n) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     if ((st = check_component(comp)) != FDTD_OK) return st;
     if (n == 0) return FDTD_OK;
@@ -1200,7 +1258,7 @@ fdtd_status_t fdtd_scatter(fdtd_solver_t* h, int comp, const int64_t* idx, const
 
 fdtd_status_t fdtd_gather(fdtd_solver_t* h, int comp, const int64_t* idx, void* values, size_t n) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     if ((st = check_component(comp)) != FDTD_OK) return st;
     if (n == 0) return FDTD_OK;
@@ -1214,7 +1272,7 @@ fdtd_status_t fdtd_gather(fdtd_solver_t* h, int comp, const int64_t* idx, void* 
 
 fdtd_status_t fdtd_read_slice(fdtd_solver_t* h, int comp, int axis, int index, void* host, size_t capacity, size_t* count_out) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     if ((st = check_component(comp)) != FDTD_OK) return st;
     if (count_out) *count_out = 0;
@@ -1239,7 +1297,7 @@ fdtd_status_t fdtd_read_slice(fdtd_solver_t* h, int comp, int axis, int index, v
 fdtd_status_t fdtd_set_source(fdtd_solver_t* h, const int lo[3], const int hi[3], const double* wx, const double* wy,
                               const double* wz, const double* amp, int n_amp) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     if (!lo || !hi || !wx || !wy || !wz || !amp || n_amp < 0) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
     const int N[3] = {s->g.Ni, s->g.Nj, s->g.Nk};
@@ -1264,7 +1322,7 @@ fdtd_status_t fdtd_set_source(fdtd_solver_t* h, const int lo[3], const int hi[3]
 
 fdtd_status_t fdtd_clear_source(fdtd_solver_t* h) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     s->src_active = false;
     return FDTD_OK;
@@ -1272,7 +1330,7 @@ fdtd_status_t fdtd_clear_source(fdtd_solver_t* h) {
 
 fdtd_status_t fdtd_sync(fdtd_solver_t* h) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     if ((st = flush_pending(s)) != FDTD_OK) return st;
     FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1281,7 +1339,7 @@ fdtd_status_t fdtd_sync(fdtd_solver_t* h) {
 
 fdtd_status_t fdtd_device_ptr(fdtd_solver_t* h, int comp, void** dptr) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     if ((st = check_component(comp)) != FDTD_OK) return st;
     if (!dptr) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
@@ -1303,7 +1361,7 @@ fdtd_status_t fdtd_get_info(fdtd_solver_t* h, fdtd_info_t* info) {
     info->pitch = s->g.pitch; info->plane = s->g.plane;
     info->device_bytes = s->device_bytes;
     info->launches = s->launches;
-    info->steps_done = s->steps_done;
+    info->steps_done = s->steps_done + s->lazy_steps;   // a recorded update_fields() call counts: it is observably done
     info->fused = s->fused ? 1 : 0;
     info->rank = s->cfg.rank; info->nranks = s->cfg.nranks; info->device = s->device;
     info->temporal = (s->t2 || s->pml_t2) ? 1 : 0;
@@ -1313,7 +1371,7 @@ fdtd_status_t fdtd_get_info(fdtd_solver_t* h, fdtd_info_t* info) {
 
 fdtd_status_t fdtd_timer_start(fdtd_solver_t* h) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     FDTD_CUDA_TRY(cudaEventRecord(s->ev_t0, s->stream));
     return FDTD_OK;
@@ -1321,7 +1379,7 @@ fdtd_status_t fdtd_timer_start(fdtd_solver_t* h) {
 
 fdtd_status_t fdtd_timer_stop(fdtd_solver_t* h, double* elapsed_ms) {
     Solver* s;
-    fdtd_status_t st = check_handle(h, &s);
+    fdtd_status_t st = enter(h, &s);
     if (st != FDTD_OK) return st;
     FDTD_CUDA_TRY(cudaEventRecord(s->ev_t1, s->stream));
     FDTD_CUDA_TRY(cudaEventSynchronize(s->ev_t1));
@@ -1333,7 +1391,10 @@ fdtd_status_t fdtd_timer_stop(fdtd_solver_t* h, double* elapsed_ms) {
 
 fdtd_status_t fdtd_get_stream(fdtd_solver_t* h, void** stream) {
     if (!h || !stream) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
-    *stream = reinterpret_cast<Solver*>(h)->stream;
+    Solver* s;
+    fdtd_status_t st = enter(h, &s);   // the caller is about to order its own work after ours
+    if (st != FDTD_OK) return st;
+    *stream = s->stream;
     return FDTD_OK;
 }
 

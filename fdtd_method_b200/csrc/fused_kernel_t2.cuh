@@ -60,6 +60,13 @@ struct FusedT2Args {
     int k_lo, k_hi;   // local planes [k_lo, k_hi) produced by this launch ...
     int k_lo2, k_hi2; // ... plus a second range (the other boundary slab of a z-slab rank; empty otherwise)
     int nz1;          // blockIdx.z < nz1 serves the first range
+    // Tile rasterisation: blockIdx.x is a linear tile id that walks strips of strip_w tile columns, row-major inside a
+    // strip (strip_w = gx, the default: plain row-major).  CTAs are dispatched in id order, one at a time as SMs free
+    // up, so the start-time skew between two tiles is about (chunk duration) x (id distance) / (CTAs in flight), and a
+    // neighbour's halo only hits L2 while that skew is short.  Both neighbours matter equally: y-neighbours share 4 of
+    // the 16 rows a tile reads, x-neighbours the two 128-byte lines at the ends of every 512-byte row (640 / 480).
+    // Narrow strips were measured and lost (profiles/strip_r01.jsonl); the host bounds the chunk length instead.
+    int gx, gy, strip_w;
     int kc;           // planes per CTA chunk
     int n_half;       // stage A: 1 or 2 half steps of B (stage B always applies 2)
     int j_quirk;      // Jx feeds all three components (FDTD_openmp semantics)
@@ -186,10 +193,21 @@ __device__ __forceinline__ void t2_update_E(T (&e)[3][V], const T (&b)[3][V], co
     }
 }
 
+template <typename T>
+__device__ __forceinline__ void t2_tile_of(const FusedT2Args<T>& a, int& bx, int& by) {
+    const int id = (int)blockIdx.x;
+    const int per = a.strip_w * a.gy;
+    const int s = id / per, r = id - s * per;
+    const int ws = min(a.strip_w, a.gx - s * a.strip_w);   // the last strip may be narrower
+    by = r / ws;
+    bx = s * a.strip_w + (r - by * ws);
+}
+
 // Per-thread constants of the pass (everything the plane iteration needs besides the register sets).
 template <typename T>
 struct T2Ctx {
     unsigned sa;            // shared address of the thread's slot in exchange array 0
+    int tile_x, tile_y;     // first column / row of the tile's footprint (halo included; CTA-uniform)
     int i, jw;
     int kb, ke;
     bool needB1, needE1, needB2, needE2, ldE, out, j_ijA, j_ijB, producer;
@@ -236,13 +254,10 @@ __device__ __forceinline__ void t2_issue_slot(const FusedT2Args<T>& a, const T2C
 // TMA flavour of the ring fill (tiles that need no periodic wrap in i / j): one thread issues six tensor copies, each
 // a {32*V cells, BY rows, 1 plane} box that lands in the slot with exactly the ring's [row][lane] layout.
 template <typename T, int BY, int SLOT>
-__device__ __forceinline__ void t2_issue_slot_tma(const FusedT2Args<T>& a, const unsigned smem0, const int kk) {
-    constexpr int V = VecOf<T>::V;
-    constexpr int TJU = BY - 4, TIU = FUSED_OUT_LANES * V;
+__device__ __forceinline__ void t2_issue_slot_tma(const FusedT2Args<T>& a, const unsigned smem0, const int x, const int y, const int kk) {
     constexpr int COMPB = BY * T2_ROWB, SLOTB = 6 * COMPB;
     const unsigned bar = smem0 + (unsigned)(t2_mbar0<BY>() + 8 * SLOT);
     const unsigned dst = smem0 + (unsigned)(8 * (BY + 2) * T2_ROWB + SLOT * SLOTB);
-    const int x = blockIdx.x * TIU - V, y = blockIdx.y * TJU - 2;
     int ke = kk + 1, kb = kk;
     if (a.g.wrap_k) {
         if (ke < 0) ke += a.g.nk; else if (ke >= a.g.nk) ke -= a.g.nk;
@@ -280,7 +295,7 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     if (TMA) {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
-        if (c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, BY, NEXT>(a, smem0, k + T2_D - 1);
+        if (c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, BY, NEXT>(a, smem0, c.tile_x, c.tile_y, k + T2_D - 1);
         mbar_wait(smem0 + (unsigned)(t2_mbar0<BY>() + 8 * SLOT), parity);
     } else {
         if (k + T2_D - 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, NEXT>(a, c, k + T2_D - 1);
@@ -418,10 +433,16 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     c.sa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)((ty + 1) * T2_ROWB + tx * 16);   // the one shared-memory address register
 
     // ---- roles ---------------------------------------------------------------------------------------------
-    c.i = blockIdx.x * TIU - V + tx * V;                    // first cell of this lane (may be -V or >= Ni)
+    {
+        int bx, by;
+        t2_tile_of(a, bx, by);
+        c.tile_x = bx * TIU - V;
+        c.tile_y = by * TJU - 2;
+    }
+    c.i = c.tile_x + tx * V;                                // first cell of this lane (may be -V or >= Ni)
     const bool lane_active = (c.i <= Ni);                   // i == Ni: right halo, wrapped to column 0
     const int iw = (c.i < 0) ? c.i + Ni : ((c.i >= Ni) ? c.i - Ni : c.i);
-    const int j = blockIdx.y * TJU - 2 + ty;
+    const int j = c.tile_y + ty;
     const bool row_active = (j <= Nj + 1);
     c.jw = j % Nj;
     if (c.jw < 0) c.jw += Nj;
@@ -462,8 +483,8 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
             for (int d = 0; d < T2_D; ++d) mbar_init(smem0 + (unsigned)(t2_mbar0<BY>() + 8 * d), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            t2_issue_slot_tma<T, BY, 0>(a, smem0, k_first);
-            if (k_first + 1 <= c.ke) t2_issue_slot_tma<T, BY, 1>(a, smem0, k_first + 1);
+            t2_issue_slot_tma<T, BY, 0>(a, smem0, c.tile_x, c.tile_y, k_first);
+            if (k_first + 1 <= c.ke) t2_issue_slot_tma<T, BY, 1>(a, smem0, c.tile_x, c.tile_y, k_first + 1);
         }
     } else {
         if (ABL != 3) t2_issue_slot<T, BY, 0>(a, c, k_first);
@@ -505,7 +526,9 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     constexpr int V = VecOf<T>::V;
     // CTA-uniform: only the few tiles whose footprint (halo included) meets the box where J may be non-zero run
     // the loop that knows about currents; tiles that need no periodic wrap in i / j load through TMA.
-    const int i0 = blockIdx.x * (FUSED_OUT_LANES * V) - V, j0 = blockIdx.y * (BY - 4) - 2;
+    int tbx, tby;
+    t2_tile_of(a, tbx, tby);
+    const int i0 = tbx * (FUSED_OUT_LANES * V) - V, j0 = tby * (BY - 4) - 2;
     // output tile = [i0 + V, i0 + V + 30 V) x [j0 + 2, j0 + BY - 2)
     if (i0 + V >= a.sb_hi[0] || i0 + V + FUSED_OUT_LANES * V <= a.sb_lo[0] || j0 + 2 >= a.sb_hi[1] || j0 + BY - 2 <= a.sb_lo[1]) return;
     const bool second = (int)blockIdx.z >= a.nz1;

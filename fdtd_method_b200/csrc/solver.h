@@ -52,6 +52,9 @@ struct Solver {
     // the missing half step is merged into the next step's leading half step (B = (B+h)+h) or applied
     // by flush() before anything reads or overwrites E/B.  Bit-identical either way.
     bool b_pending = false;
+    // Lazy pairing of single update_fields() calls: an odd call is only recorded; the next call runs both as one
+    // two-step pass, and every other entry point that reads or changes solver state runs the recorded step first.
+    int lazy_steps = 0;
     bool ghosts_e_valid = false;   // top ghost planes of Ex, Ey hold the upper neighbour's current plane
     bool ghosts_b_valid = false;   // bottom ghost planes of Bx, By hold the lower neighbour's current plane
     bool ghosts_fused_valid = false;

@@ -133,7 +133,11 @@ fdtd_status_t fdtd_destroy(fdtd_solver_t* s);
 /* ---- the hot path ------------------------------------------------------- */
 
 /* FDTD::update_fields() / FDTD_PML::update_fields(): one Yee step (B half, E, B half).
- * Asynchronous on the solver's stream; field reads below synchronise as needed. */
+ * Asynchronous on the solver's stream; field reads below synchronise as needed.
+ * Caller loops that step one call at a time still reach the two-step pass: an odd call is recorded and returns at
+ * once, the next call issues both steps together; every other call of this API that reads or changes solver state
+ * runs the recorded step first, so the observable sequence is exactly one step per call.  A CUDA error of a recorded
+ * step is reported by the call that runs it.  (FDTD_B200_NO_LAZY=1 in the environment issues every call at once.) */
 fdtd_status_t fdtd_update_fields(fdtd_solver_t* s);
 
 /* nsteps x update_fields().  Bit-identical to nsteps separate calls. */

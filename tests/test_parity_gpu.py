@@ -58,6 +58,40 @@ def test_update_fields_one_by_one_equals_step_n():
     assert_bit_equal(o, g, what="final")
 
 
+def test_update_fields_loop_pairs_lazily(monkeypatch):
+    """Reference-style caller loops (`for (...) solver.update_fields();`) reach the two-step pass: an odd call is
+    recorded, the next one issues both steps; any state access in between runs the recorded step first."""
+    Ni, Nj, Nk = 32, 16, 12
+    o, g = make_pair(Ni, Nj, Nk)
+    f = seeded_fields(4, (Nk, Nj, Ni), same_j=False)
+    load_both(o, g, f)
+    for _ in range(7):
+        o.update_fields()
+        g.update_fields()
+    info = g.info()
+    assert info.steps_done == 7 and info.passes_t2 == 3     # three pairs issued, the 7th call recorded
+    assert_bit_equal(o, g, what="7 calls")                   # the download runs the recorded step
+    assert g.info().passes_t2 == 3
+    # a J write between two calls: the recorded step must still see the old J
+    o.update_fields(); g.update_fields()
+    idx = np.array([5, 77, 300, Ni * Nj * Nk - 1])
+    vals = np.array([0.5, -1.5, 2.0, 3.0])
+    for c in (6, 7, 8):
+        g.scatter(c, idx, vals * (c - 5))
+        o.field(c).reshape(-1)[idx] = vals * (c - 5)
+    o.update_fields(); g.update_fields()
+    o.update_fields(); g.update_fields()
+    assert_bit_equal(o, g, what="J write between calls")
+    # switched off: every call is issued at once, same bits
+    monkeypatch.setenv("FDTD_B200_NO_LAZY", "1")
+    o2, g2 = make_pair(Ni, Nj, Nk)
+    load_both(o2, g2, f)
+    for _ in range(4):
+        o2.update_fields(); g2.update_fields()
+    assert g2.info().passes_t2 == 0
+    assert_bit_equal(o2, g2, what="no lazy")
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("fusion", [True, False])
 def test_dtype_modes(dtype, fusion):

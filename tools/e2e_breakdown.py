@@ -91,6 +91,13 @@ if __name__ == "__main__":
 
     block()
     out["step_block_ms_per_step"] = 1e3 * wall(block, 1) / a.steps
+    def loop():
+        for _ in range(a.steps):
+            g.update_fields()      # reference-style caller loop: pairs lazily into the two-step pass
+        g.sync()
+
+    loop()
+    out["update_fields_loop_ms_per_step"] = 1e3 * wall(loop, 1) / a.steps
     print(json.dumps(out), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/e2e_breakdown.json", "w") as fh:

@@ -5,7 +5,7 @@ out=gpurun_out/$tag
 mkdir -p $out
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $out/pytest_gpu.log 2>&1
 tail -3 $out/pytest_gpu.log
-timeout 900 python tools/config_table.py --skip-1024 --quick > $out/config_table.jsonl 2> $out/config_table.err
+timeout 900 python tools/config_table.py --quick > $out/config_table.jsonl 2> $out/config_table.err
 cat $out/config_table.jsonl
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file $out/launches_pml.csv \
     python bench.py --workload pml --steps 4 --warmup 3 --no-cpu > $out/bench_pml_under_ncu.log 2>&1
