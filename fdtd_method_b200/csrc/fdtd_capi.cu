@@ -295,10 +295,10 @@ static int t2_variant() {
 
 template <typename T, int BY, int MINB, int ABL = 0>
 static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
-    constexpr int V = VecOf<T>::V;
+    constexpr int V = T2_V;   // 2 cells per lane for both storage types
     constexpr int TIU = FUSED_OUT_LANES * V;
     constexpr int TJU = BY - 4;
-    constexpr size_t smem = fused_t2_smem_bytes<BY>();
+    constexpr size_t smem = fused_t2_smem_bytes<T, BY>();
     static bool configured[16] = {};
     if (!configured[s->device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, MINB, true, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -374,13 +374,13 @@ static tmap_encode_fn tmap_encoder() {
     return fn;
 }
 
-// 3-D tensor map of one component array of generation `gen` (ghost planes included), box = {32*V, by, 1}.
+// 3-D tensor map of one component array of generation `gen` (ghost planes included), box = {64 cells, by rows, 1 plane}.
 static bool encode_tmap(const Solver* s, CUtensorMap* tm, int comp, int gen, int by) {
     tmap_encode_fn enc = tmap_encoder();
     if (!enc) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)s->g.Ni, (cuuint64_t)s->g.Nj, (cuuint64_t)(s->g.nk + 2 * GHOST_PLANES)};
     const cuuint64_t strides[2] = {(cuuint64_t)s->g.pitch * s->esz, (cuuint64_t)s->g.plane * s->esz};
-    const cuuint32_t box[3] = {(cuuint32_t)(FUSED_BX * (16 / s->esz)), (cuuint32_t)by, 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)(s->esz == 8 ? t2_rbox<double>() : t2_rbox<float>()), (cuuint32_t)by, 1u};   // 64 cells = 512 B (fp64) / 68 cells = 272 B (fp32)
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (box[0] > (cuuint32_t)s->g.Ni || by > s->g.Nj) return false;   // no wrap-free tile exists anyway
     const CUresult r = enc(tm, s->esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,

@@ -13,10 +13,15 @@
 // read E0(3)+B0(3), write E2(3)+B2(3) = 12 words per cell per TWO steps = 6 words (48 B fp64) per
 // cell-step, against 12 for the one-step fused pass and 30 for the reference's three sweeps.
 //
-// Tile roles (V = cells per 16-byte vector; the dependency cone of one output cell reaches 2 cells down
-// and 2 cells up in i, j and k):
+// Storage vs arithmetic: V = 2 cells per lane for BOTH storage types.  Registers and the shared-memory row exchanges
+// always hold doubles; only the ring (raw bytes copied from global memory) and the global loads / stores are in the
+// storage type.  fp32 storage ("float storage, double arithmetic") therefore converts each input once
+// when it leaves the ring and rounds each produced value once (double -> float -> double), instead of converting
+// at every use -- F2F runs at 16 per clock per SM and was the bound of the first fp32 version of this pass.
+//
+// Tile roles (the dependency cone of one output cell reaches 2 cells down and 2 cells up in i, j and k):
 //   * warp = 32 lanes x V cells of one row; lane 0 / lane 31 are the left / right halo lanes
-//     (2 halo cells fit in one lane for V = 2 and V = 4), lanes 1..30 store -> 30*V cells per row;
+//     (the 2 halo cells fit in one lane), lanes 1..30 store -> 30*V = 60 cells per row;
 //     i-neighbours travel by __shfl_up/down (north_star (b));
 //   * CTA = BY warps = BY consecutive rows; rows 0,1 and BY-2,BY-1 are halo rows, rows 2..BY-3 store;
 //     j-neighbours travel through four single-buffered shared-memory row exchanges (E0, B1, E1, B2),
@@ -90,14 +95,21 @@ struct FusedT2Args {
 // ---- shared-memory plumbing ---------------------------------------------------------------------------------
 // Every shared access of a thread is [sa + compile-time offset] (one address register): exchange arrays are
 // (BY + 2) rows so that "one row up / down" is +-512 B with no clamping, the ring follows.
-constexpr int T2_ROWB = FUSED_BX * 16;   // bytes per exchange / ring row (32 lanes x 16 B)
+constexpr int T2_V = 2;                  // cells per lane
+constexpr int T2_ROWB = FUSED_BX * 16;   // bytes per exchange row (32 lanes x 2 doubles)
+// Ring rows hold raw storage.  fp64: 64 cells = 512 B, the tile's footprint starts at byte 480*bx - 16 of a row.  fp32: the
+// footprint starts at byte 240*bx - 8, but a TMA box must start on a 16-byte boundary in global memory, so the box
+// starts 2 cells earlier and is 68 cells (272 B) wide; lane tx reads bytes [8 + 8 tx, 16 + 8 tx) of its ring row.
+template <typename T> __host__ __device__ constexpr int t2_rbox() { return sizeof(T) == 8 ? FUSED_BX * T2_V : FUSED_BX * T2_V + 4; }   // cells per ring row
+template <typename T> __host__ __device__ constexpr int t2_rskip() { return sizeof(T) == 8 ? 0 : 2; }                                  // cells before lane 0
+template <typename T> __host__ __device__ constexpr int t2_rrowb() { return t2_rbox<T>() * (int)sizeof(T); }                            // bytes per ring row
 template <int BY> __host__ __device__ constexpr int t2_xq(int q) { return q * (BY + 2) * T2_ROWB; }          // exchange array q, own slot
-template <int BY> __host__ __device__ constexpr int t2_ring0() { return 8 * (BY + 2) * T2_ROWB - T2_ROWB; }   // ring slot 0 comp 0, rel. to sa
+template <int BY> __host__ __device__ constexpr int t2_ringbase() { return 8 * (BY + 2) * T2_ROWB; }         // absolute offset of ring slot 0 comp 0
 constexpr int T2_D = 3;                  // ring depth = unroll factor of the k loop
-template <int BY> __host__ __device__ constexpr int t2_mbar0() { return (8 * (BY + 2) + T2_D * 6 * BY) * T2_ROWB; }   // absolute
-template <int BY>
+template <typename T, int BY> __host__ __device__ constexpr int t2_mbar0() { return t2_ringbase<BY>() + T2_D * 6 * BY * t2_rrowb<T>(); }   // absolute
+template <typename T, int BY>
 constexpr size_t fused_t2_smem_bytes() {
-    return (size_t)t2_mbar0<BY>() + 64;
+    return (size_t)t2_mbar0<T, BY>() + 64;
 }
 
 // ---- mbarrier / TMA primitives --------------------------------------------------------------------------------
@@ -123,8 +135,8 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm,
                  ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
-template <typename T> struct SmemIO;
-template <> struct SmemIO<double> {
+// Exchange arrays: always doubles.
+struct XIO {
     template <int OFF> static __device__ __forceinline__ void ld(unsigned a, double (&v)[2]) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v[0]), "=d"(v[1]) : "r"(a), "n"(OFF) : "memory");
     }
@@ -132,36 +144,61 @@ template <> struct SmemIO<double> {
         asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v[0]), "d"(v[1]) : "memory");
     }
 };
-template <> struct SmemIO<float> {
-    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, float (&v)[4]) {
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
-                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a), "n"(OFF) : "memory");
-    }
-    template <int OFF> static __device__ __forceinline__ void st(unsigned a, const float (&v)[4]) {
-        asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+// Ring: raw storage, converted once on the way into registers.
+template <typename T> struct RingIO;
+template <> struct RingIO<double> {
+    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, double (&v)[2]) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v[0]), "=d"(v[1]) : "r"(a), "n"(OFF) : "memory");
     }
 };
+template <> struct RingIO<float> {
+    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, double (&v)[2]) {
+        float f0, f1;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(f0), "=f"(f1) : "r"(a), "n"(OFF) : "memory");
+        v[0] = (double)f0; v[1] = (double)f1;
+    }
+};
+// Global memory: 2 cells of storage type <-> 2 doubles.
+__device__ __forceinline__ void t2_ldg(const double* p, double (&o)[2]) {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    o[0] = v.x; o[1] = v.y;
+}
+__device__ __forceinline__ void t2_ldg(const float* p, double (&o)[2]) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    o[0] = (double)v.x; o[1] = (double)v.y;
+}
+template <bool CS> __device__ __forceinline__ void t2_stg(double* p, const double (&o)[2]) {
+    if (CS) __stcs(reinterpret_cast<double2*>(p), make_double2(o[0], o[1]));
+    else *reinterpret_cast<double2*>(p) = make_double2(o[0], o[1]);
+}
+template <bool CS> __device__ __forceinline__ void t2_stg(float* p, const double (&o)[2]) {   // values are already float-representable
+    if (CS) __stcs(reinterpret_cast<float2*>(p), make_float2((float)o[0], (float)o[1]));
+    else *reinterpret_cast<float2*>(p) = make_float2((float)o[0], (float)o[1]);
+}
+
 // B += n_half * h(E)   (FDTD.cpp:121-126).  e = E(k), ek = E(k+1), (ezu, exu) = Ez, Ex one row up,
 // (ez_nl, ey_nl) = Ez, Ey first element of the next lane.
-template <typename T, int V>
-__device__ __forceinline__ void t2_update_B(T (&b)[3][V], const T (&e)[3][V], const T (&ek)[3][V], const T (&ezu)[V],
-                                            const T (&exu)[V], const T ez_nl, const T ey_nl, const double cBx,
-                                            const double cBy, const double cBz, const bool two) {
+template <typename T>
+__device__ __forceinline__ void t2_update_B(double (&b)[3][T2_V], const double (&e)[3][T2_V], const double (&ek)[3][T2_V],
+                                            const double (&ezu)[T2_V], const double (&exu)[T2_V], const double ez_nl,
+                                            const double ey_nl, const double cBx, const double cBy, const double cBz,
+                                            const bool two) {
+    constexpr int V = T2_V;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
-        const double ex = (double)e[0][q], ey = (double)e[1][q], ez = (double)e[2][q];
-        const double ezr = (double)((q == V - 1) ? ez_nl : e[2][(q + 1) % V]);
-        const double eyr = (double)((q == V - 1) ? ey_nl : e[1][(q + 1) % V]);
-        const double hx = dsub(dmul(cBz, dsub((double)ek[1][q], ey)), dmul(cBy, dsub((double)ezu[q], ez)));
-        const double hy = dsub(dmul(cBx, dsub(ezr, ez)), dmul(cBz, dsub((double)ek[0][q], ex)));
-        const double hz = dsub(dmul(cBy, dsub((double)exu[q], ex)), dmul(cBx, dsub(eyr, ey)));
-        T nbx = (T)dadd((double)b[0][q], hx);
-        T nby = (T)dadd((double)b[1][q], hy);
-        T nbz = (T)dadd((double)b[2][q], hz);
+        const double ex = e[0][q], ey = e[1][q], ez = e[2][q];
+        const double ezr = (q == V - 1) ? ez_nl : e[2][(q + 1) % V];
+        const double eyr = (q == V - 1) ? ey_nl : e[1][(q + 1) % V];
+        const double hx = dsub(dmul(cBz, dsub(ek[1][q], ey)), dmul(cBy, dsub(ezu[q], ez)));
+        const double hy = dsub(dmul(cBx, dsub(ezr, ez)), dmul(cBz, dsub(ek[0][q], ex)));
+        const double hz = dsub(dmul(cBy, dsub(exu[q], ex)), dmul(cBx, dsub(eyr, ey)));
+        double nbx = round_store<T>(dadd(b[0][q], hx));
+        double nby = round_store<T>(dadd(b[1][q], hy));
+        double nbz = round_store<T>(dadd(b[2][q], hz));
         if (two) {
-            nbx = (T)dadd((double)nbx, hx);
-            nby = (T)dadd((double)nby, hy);
-            nbz = (T)dadd((double)nbz, hz);
+            nbx = round_store<T>(dadd(nbx, hx));
+            nby = round_store<T>(dadd(nby, hy));
+            nbz = round_store<T>(dadd(nbz, hz));
         }
         b[0][q] = nbx; b[1][q] = nby; b[2][q] = nbz;
     }
@@ -169,27 +206,28 @@ __device__ __forceinline__ void t2_update_B(T (&b)[3][V], const T (&e)[3][V], co
 
 // E += g(B, J)   (FDTD.cpp:85-93 / kokkos_functors.h:81-89), in place.  b = B(k), (bxk, byk) = Bx, By at k-1,
 // (bzd, bxd) = Bz, Bx one row down, (bz_pl, by_pl) = Bz, By last element of the previous lane.
-template <typename T, int V>
-__device__ __forceinline__ void t2_update_E(T (&e)[3][V], const T (&b)[3][V], const T (&bxk)[V], const T (&byk)[V],
-                                            const T (&bzd)[V], const T (&bxd)[V], const T bz_pl, const T by_pl,
-                                            const double cEx, const double cEy, const double cEz, const double cJ,
-                                            const bool use_j, const T (&jv)[3][V]) {
+template <typename T>
+__device__ __forceinline__ void t2_update_E(double (&e)[3][T2_V], const double (&b)[3][T2_V], const double (&bxk)[T2_V],
+                                            const double (&byk)[T2_V], const double (&bzd)[T2_V], const double (&bxd)[T2_V],
+                                            const double bz_pl, const double by_pl, const double cEx, const double cEy,
+                                            const double cEz, const double cJ, const bool use_j, const double (&jv)[3][T2_V]) {
+    constexpr int V = T2_V;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
-        const double bx = (double)b[0][q], by = (double)b[1][q], bz = (double)b[2][q];
-        const double bzl = (double)((q == 0) ? bz_pl : b[2][(q + V - 1) % V]);
-        const double byl = (double)((q == 0) ? by_pl : b[1][(q + V - 1) % V]);
-        double tx_ = dmul(cEy, dsub(bz, (double)bzd[q]));
-        double ty_ = dmul(cEz, dsub(bx, (double)bxk[q]));
+        const double bx = b[0][q], by = b[1][q], bz = b[2][q];
+        const double bzl = (q == 0) ? bz_pl : b[2][(q + V - 1) % V];
+        const double byl = (q == 0) ? by_pl : b[1][(q + V - 1) % V];
+        double tx_ = dmul(cEy, dsub(bz, bzd[q]));
+        double ty_ = dmul(cEz, dsub(bx, bxk[q]));
         double tz_ = dmul(cEx, dsub(by, byl));
         if (use_j) {
-            tx_ = dadd(dmul(cJ, (double)jv[0][q]), tx_);
-            ty_ = dadd(dmul(cJ, (double)jv[1][q]), ty_);
-            tz_ = dadd(dmul(cJ, (double)jv[2][q]), tz_);
+            tx_ = dadd(dmul(cJ, jv[0][q]), tx_);
+            ty_ = dadd(dmul(cJ, jv[1][q]), ty_);
+            tz_ = dadd(dmul(cJ, jv[2][q]), tz_);
         }
-        e[0][q] = (T)dadd((double)e[0][q], dsub(tx_, dmul(cEz, dsub(by, (double)byk[q]))));
-        e[1][q] = (T)dadd((double)e[1][q], dsub(ty_, dmul(cEx, dsub(bz, bzl))));
-        e[2][q] = (T)dadd((double)e[2][q], dsub(tz_, dmul(cEy, dsub(bx, (double)bxd[q]))));
+        e[0][q] = round_store<T>(dadd(e[0][q], dsub(tx_, dmul(cEz, dsub(by, byk[q])))));
+        e[1][q] = round_store<T>(dadd(e[1][q], dsub(ty_, dmul(cEx, dsub(bz, bzl)))));
+        e[2][q] = round_store<T>(dadd(e[2][q], dsub(tz_, dmul(cEy, dsub(bx, bxd[q])))));
     }
 }
 
@@ -207,6 +245,7 @@ __device__ __forceinline__ void t2_tile_of(const FusedT2Args<T>& a, int& bx, int
 template <typename T>
 struct T2Ctx {
     unsigned sa;            // shared address of the thread's slot in exchange array 0
+    unsigned sr;            // shared address of the thread's entry in ring slot 0, component 0 (= sa + constant for fp64)
     int tile_x, tile_y;     // first column / row of the tile's footprint (halo included; CTA-uniform)
     int i, jw;
     int kb, ke;
@@ -225,39 +264,41 @@ __device__ __forceinline__ long long t2_plane_of(const FusedT2Args<T>& a, int k)
     return (long long)k * a.g.plane;
 }
 
-template <int OFF>
-__device__ __forceinline__ void cp_async16_at(unsigned a, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0+%1], [%2], 16;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
+// One lane's 2 cells of one ring row: 16 bytes (fp64, L1 bypass) or 8 bytes (fp32).
+template <typename T, int OFF>
+__device__ __forceinline__ void t2_cp_async_at(unsigned a, const T* gmem_src) {
+    if (sizeof(T) == 8) asm volatile("cp.async.cg.shared.global [%0+%1], [%2], 16;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0+%1], [%2], 8;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
 }
 
-// Asynchronous copies (LDGSTS, L1 bypass) of plane iteration kk into ring slot SLOT: old E(kk+1) and, for the rows
+// Asynchronous copies (LDGSTS) of plane iteration kk into ring slot SLOT: old E(kk+1) and, for the rows
 // that produce B1, B0(kk).  Every thread copies the six vectors it will read back itself, so the ring needs no
 // barrier, only cp.async.wait_group.
 template <typename T, int BY, int SLOT>
 __device__ __forceinline__ void t2_issue_slot(const FusedT2Args<T>& a, const T2Ctx<T>& c, const int kk) {
-    constexpr int COMPB = BY * T2_ROWB, SLOTB = 6 * COMPB;
-    constexpr int RING = t2_ring0<BY>() + SLOT * SLOTB;
+    constexpr int COMPB = BY * t2_rrowb<T>(), SLOTB = 6 * COMPB;
+    constexpr int RING = SLOT * SLOTB;
     if (c.ldE) {
         const long long pe = t2_plane_of(a, kk + 1) + c.roff;
-        cp_async16_at<RING + 0 * COMPB>(c.sa, a.Ein[0] + pe);
-        cp_async16_at<RING + 1 * COMPB>(c.sa, a.Ein[1] + pe);
-        cp_async16_at<RING + 2 * COMPB>(c.sa, a.Ein[2] + pe);
+        t2_cp_async_at<T, RING + 0 * COMPB>(c.sr, a.Ein[0] + pe);
+        t2_cp_async_at<T, RING + 1 * COMPB>(c.sr, a.Ein[1] + pe);
+        t2_cp_async_at<T, RING + 2 * COMPB>(c.sr, a.Ein[2] + pe);
         if (c.needB1) {
             const long long pb = t2_plane_of(a, kk) + c.roff;
-            cp_async16_at<RING + 3 * COMPB>(c.sa, a.Bin[0] + pb);
-            cp_async16_at<RING + 4 * COMPB>(c.sa, a.Bin[1] + pb);
-            cp_async16_at<RING + 5 * COMPB>(c.sa, a.Bin[2] + pb);
+            t2_cp_async_at<T, RING + 3 * COMPB>(c.sr, a.Bin[0] + pb);
+            t2_cp_async_at<T, RING + 4 * COMPB>(c.sr, a.Bin[1] + pb);
+            t2_cp_async_at<T, RING + 5 * COMPB>(c.sr, a.Bin[2] + pb);
         }
     }
 }
 
 // TMA flavour of the ring fill (tiles that need no periodic wrap in i / j): one thread issues six tensor copies, each
-// a {32*V cells, BY rows, 1 plane} box that lands in the slot with exactly the ring's [row][lane] layout.
+// a {t2_rbox cells, BY rows, 1 plane} box that lands in the slot with exactly the ring's [row][lane] layout.
 template <typename T, int BY, int SLOT>
 __device__ __forceinline__ void t2_issue_slot_tma(const FusedT2Args<T>& a, const unsigned smem0, const int x, const int y, const int kk) {
-    constexpr int COMPB = BY * T2_ROWB, SLOTB = 6 * COMPB;
-    const unsigned bar = smem0 + (unsigned)(t2_mbar0<BY>() + 8 * SLOT);
-    const unsigned dst = smem0 + (unsigned)(8 * (BY + 2) * T2_ROWB + SLOT * SLOTB);
+    constexpr int COMPB = BY * t2_rrowb<T>(), SLOTB = 6 * COMPB;
+    const unsigned bar = smem0 + (unsigned)(t2_mbar0<T, BY>() + 8 * SLOT);
+    const unsigned dst = smem0 + (unsigned)(t2_ringbase<BY>() + SLOT * SLOTB);
     int ke = kk + 1, kb = kk;
     if (a.g.wrap_k) {
         if (ke < 0) ke += a.g.nk; else if (ke >= a.g.nk) ke -= a.g.nk;
@@ -266,8 +307,8 @@ __device__ __forceinline__ void t2_issue_slot_tma(const FusedT2Args<T>& a, const
     mbar_arrive_expect_tx(bar, (unsigned)(6 * COMPB));
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-        tma_load_3d(dst + q * COMPB, &a.tmE[q], x, y, ke + GHOST_PLANES, bar);
-        tma_load_3d(dst + (3 + q) * COMPB, &a.tmB[q], x, y, kb + GHOST_PLANES, bar);
+        tma_load_3d(dst + q * COMPB, &a.tmE[q], x - t2_rskip<T>(), y, ke + GHOST_PLANES, bar);
+        tma_load_3d(dst + (3 + q) * COMPB, &a.tmB[q], x - t2_rskip<T>(), y, kb + GHOST_PLANES, bar);
     }
 }
 
@@ -276,18 +317,19 @@ __device__ __forceinline__ void t2_issue_slot_tma(const FusedT2Args<T>& a, const
 //   b  : free -> B0(k) -> B1(k)        b1 : B1(k-1) -> B2(k-1) (stored)  b2 : B2(k-2) (x, y used)
 template <typename T, int BY, bool TWO_A, bool HAS_J, bool TMA, int ABL, int SLOT>
 __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>& c, const int k, const unsigned parity,
-                                         T (&en)[3][VecOf<T>::V], T (&e0)[3][VecOf<T>::V], T (&e1)[3][VecOf<T>::V],
-                                         T (&b)[3][VecOf<T>::V], T (&b1)[3][VecOf<T>::V], T (&b2)[3][VecOf<T>::V]) {
-    constexpr int V = VecOf<T>::V;
+                                         double (&en)[3][T2_V], double (&e0)[3][T2_V], double (&e1)[3][T2_V],
+                                         double (&b)[3][T2_V], double (&b1)[3][T2_V], double (&b2)[3][T2_V]) {
+    constexpr int V = T2_V;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int UP = T2_ROWB, DN = -T2_ROWB;
     constexpr int XE0z = t2_xq<BY>(0), XE0x = t2_xq<BY>(1), XB1z = t2_xq<BY>(2), XB1x = t2_xq<BY>(3);
     constexpr int XE1z = t2_xq<BY>(4), XE1x = t2_xq<BY>(5), XB2z = t2_xq<BY>(6), XB2x = t2_xq<BY>(7);
-    constexpr int COMPB = BY * T2_ROWB, SLOTB = 6 * COMPB;
-    constexpr int RING = t2_ring0<BY>() + SLOT * SLOTB;
+    constexpr int COMPB = BY * t2_rrowb<T>(), SLOTB = 6 * COMPB;
+    constexpr int RING = SLOT * SLOTB;                 // relative to c.sr
     constexpr int NEXT = (SLOT + T2_D - 1) % T2_D;     // slot freed by the previous plane
-    using IO = SmemIO<T>;
-    const unsigned sa = c.sa;
+    using IO = XIO;
+    using RIO = RingIO<T>;
+    const unsigned sa = c.sa, sr = c.sr;
     const double cBx = a.c.cBx, cBy = a.c.cBy, cBz = a.c.cBz;
     const double cEx = a.c.cEx, cEy = a.c.cEy, cEz = a.c.cEz, cJ = a.c.cJ;
 
@@ -296,25 +338,25 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
         extern __shared__ __align__(16) unsigned char smem_raw[];
         const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
         if (c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, BY, NEXT>(a, smem0, c.tile_x, c.tile_y, k + T2_D - 1);
-        mbar_wait(smem0 + (unsigned)(t2_mbar0<BY>() + 8 * SLOT), parity);
+        mbar_wait(smem0 + (unsigned)(t2_mbar0<T, BY>() + 8 * SLOT), parity);
     } else {
         if (k + T2_D - 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, NEXT>(a, c, k + T2_D - 1);
         cp_async_commit();
         cp_async_wait<T2_D - 1>();
     }
-    IO::template ld<RING + 1 * COMPB>(sa, en[1]);
-    IO::template ld<RING + 0 * COMPB>(sa, en[0]);
-    IO::template ld<RING + 2 * COMPB>(sa, en[2]);
+    RIO::template ld<RING + 1 * COMPB>(sr, en[1]);
+    RIO::template ld<RING + 0 * COMPB>(sr, en[0]);
+    RIO::template ld<RING + 2 * COMPB>(sr, en[2]);
     if (c.needB1) {
-        IO::template ld<RING + 3 * COMPB>(sa, b[0]);
-        IO::template ld<RING + 4 * COMPB>(sa, b[1]);
-        IO::template ld<RING + 5 * COMPB>(sa, b[2]);
-        T ezu[V], exu[V];
+        RIO::template ld<RING + 3 * COMPB>(sr, b[0]);
+        RIO::template ld<RING + 4 * COMPB>(sr, b[1]);
+        RIO::template ld<RING + 5 * COMPB>(sr, b[2]);
+        double ezu[V], exu[V];
         IO::template ld<XE0z + UP>(sa, ezu);
         IO::template ld<XE0x + UP>(sa, exu);
-        const T ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
-        const T ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
-        if (ABL != 4) t2_update_B<T, V>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, TWO_A);
+        const double ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
+        const double ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
+        if (ABL != 4) t2_update_B<T>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, TWO_A);
         IO::template st<XB1z>(sa, b[2]);
         IO::template st<XB1x>(sa, b[0]);
     }
@@ -324,11 +366,11 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     IO::template st<XE0z>(sa, en[2]);   // old E(k+1) rows for the next plane's phase X
     IO::template st<XE0x>(sa, en[0]);
     if (c.needE1) {
-        T bzd[V], bxd[V], jv[3][V];
+        double bzd[V], bxd[V], jv[3][V];
         IO::template ld<XB1z + DN>(sa, bzd);
         IO::template ld<XB1x + DN>(sa, bxd);
-        const T bz_pl = __shfl_up_sync(FULL, b[2][V - 1], 1);
-        const T by_pl = __shfl_up_sync(FULL, b[1][V - 1], 1);
+        const double bz_pl = __shfl_up_sync(FULL, b[2][V - 1], 1);
+        const double by_pl = __shfl_up_sync(FULL, b[1][V - 1], 1);
         bool use_j = false;
         if (HAS_J) {
             // J of step s applies to E1(k) on owned planes and on the halo planes that recompute a neighbour's
@@ -338,22 +380,22 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
             use_j = c.j_ijA && (kgw >= a.jbox.lo[2]) && (kgw < a.jbox.hi[2]);
             if (use_j) {
                 const long long pj = t2_plane_of(a, k) + c.roff;
-                ldg_vec<T, V>(a.J[0] + pj, jv[0]);
-                ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
-                ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
+                t2_ldg(a.J[0] + pj, jv[0]);
+                t2_ldg((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
+                t2_ldg((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
             }
         }
         // e0 (= old E(k)) becomes E1(k) in place
-        if (ABL != 4) t2_update_E<T, V>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+        if (ABL != 4) t2_update_E<T>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
     }
     if (c.needB2) {
-        T ezu[V], exu[V];
+        double ezu[V], exu[V];
         IO::template ld<XE1z + UP>(sa, ezu);   // E1(k-1) one row up (written in phase Z of the previous plane)
         IO::template ld<XE1x + UP>(sa, exu);
-        const T ez_nl = __shfl_down_sync(FULL, e1[2][0], 1);
-        const T ey_nl = __shfl_down_sync(FULL, e1[1][0], 1);
+        const double ez_nl = __shfl_down_sync(FULL, e1[2][0], 1);
+        const double ey_nl = __shfl_down_sync(FULL, e1[1][0], 1);
         // b1 (= B1(k-1)) becomes B2(k-1) in place
-        if (ABL != 4) t2_update_B<T, V>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
+        if (ABL != 4) t2_update_B<T>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
         IO::template st<XB2z>(sa, b1[2]);
         IO::template st<XB2x>(sa, b1[0]);
     }
@@ -365,11 +407,11 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
         IO::template st<XE1x>(sa, e0[0]);
     }
     if (c.needE2) {
-        T bzd[V], bxd[V], jv[3][V];
+        double bzd[V], bxd[V], jv[3][V];
         IO::template ld<XB2z + DN>(sa, bzd);
         IO::template ld<XB2x + DN>(sa, bxd);
-        const T bz_pl = __shfl_up_sync(FULL, b1[2][V - 1], 1);
-        const T by_pl = __shfl_up_sync(FULL, b1[1][V - 1], 1);
+        const double bz_pl = __shfl_up_sync(FULL, b1[2][V - 1], 1);
+        const double by_pl = __shfl_up_sync(FULL, b1[1][V - 1], 1);
         const int kB = k - 1;                          // plane of stage B (an owned plane whenever it is stored)
         const bool stored = (kB >= c.kb);
         bool use_j = false;
@@ -378,16 +420,16 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
             use_j = c.j_ijB && stored && (kgB >= a.jbox.lo[2]) && (kgB < a.jbox.hi[2]);
             if (use_j) {
                 const long long pj = (long long)kB * a.g.plane + c.roff;
-                ldg_vec<T, V>(a.J[0] + pj, jv[0]);
-                ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
-                ldg_vec<T, V>((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
+                t2_ldg(a.J[0] + pj, jv[0]);
+                t2_ldg((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
+                t2_ldg((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
                 if (a.src2 && kgB >= a.s_lo[2] && kgB < a.s_hi[2] && c.jw >= a.s_lo[1] && c.jw < a.s_hi[1]) {
                     const double wy = a.sw[1][c.jw - a.s_lo[1]], wz = a.sw[2][kgB - a.s_lo[2]];
 #pragma unroll
                     for (int q = 0; q < V; ++q) {
                         const int ii = c.i + q;
                         if (ii >= a.s_lo[0] && ii < a.s_hi[0]) {
-                            const T v = (T)dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wy), wz);
+                            const double v = round_store<T>(dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wy), wz));
                             jv[0][q] = v; jv[1][q] = v; jv[2][q] = v;
                         }
                     }
@@ -395,23 +437,23 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
             }
         }
         // e1 (= E1(k-1)) becomes E2(k-1) in place
-        if (ABL != 4) t2_update_E<T, V>(e1, b1, b2[0], b2[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+        if (ABL != 4) t2_update_E<T>(e1, b1, b2[0], b2[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
         if (c.out && stored && ABL != 2) {
             const long long o = (long long)kB * a.g.plane + c.roff;
             if (a.st_cs) {
-                stg_vec_cs<T, V>(a.Eout[0] + o, e1[0]);
-                stg_vec_cs<T, V>(a.Eout[1] + o, e1[1]);
-                stg_vec_cs<T, V>(a.Eout[2] + o, e1[2]);
-                stg_vec_cs<T, V>(a.Bout[0] + o, b1[0]);
-                stg_vec_cs<T, V>(a.Bout[1] + o, b1[1]);
-                stg_vec_cs<T, V>(a.Bout[2] + o, b1[2]);
+                t2_stg<true>(a.Eout[0] + o, e1[0]);
+                t2_stg<true>(a.Eout[1] + o, e1[1]);
+                t2_stg<true>(a.Eout[2] + o, e1[2]);
+                t2_stg<true>(a.Bout[0] + o, b1[0]);
+                t2_stg<true>(a.Bout[1] + o, b1[1]);
+                t2_stg<true>(a.Bout[2] + o, b1[2]);
             } else {
-                stg_vec<T, V>(a.Eout[0] + o, e1[0]);
-                stg_vec<T, V>(a.Eout[1] + o, e1[1]);
-                stg_vec<T, V>(a.Eout[2] + o, e1[2]);
-                stg_vec<T, V>(a.Bout[0] + o, b1[0]);
-                stg_vec<T, V>(a.Bout[1] + o, b1[1]);
-                stg_vec<T, V>(a.Bout[2] + o, b1[2]);
+                t2_stg<false>(a.Eout[0] + o, e1[0]);
+                t2_stg<false>(a.Eout[1] + o, e1[1]);
+                t2_stg<false>(a.Eout[2] + o, e1[2]);
+                t2_stg<false>(a.Bout[0] + o, b1[0]);
+                t2_stg<false>(a.Bout[1] + o, b1[1]);
+                t2_stg<false>(a.Bout[2] + o, b1[2]);
             }
         }
     }
@@ -419,10 +461,10 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
 
 template <typename T, int BY, bool TWO_A, bool HAS_J, bool TMA, int ABL>
 __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
-    constexpr int V = VecOf<T>::V;
+    constexpr int V = T2_V;
     constexpr int TJU = BY - 4;               // output rows per CTA
     constexpr int TIU = FUSED_OUT_LANES * V;  // output cells per CTA row
-    using IO = SmemIO<T>;
+    using IO = XIO;
     static_assert(BY >= 5, "T2 pass needs at least one output row");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -430,7 +472,9 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int Ni = a.g.Ni, Nj = a.g.Nj;
     T2Ctx<T> c;
-    c.sa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)((ty + 1) * T2_ROWB + tx * 16);   // the one shared-memory address register
+    c.sa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)((ty + 1) * T2_ROWB + tx * 16);   // the one shared-memory address register ...
+    if (sizeof(T) == 8) c.sr = c.sa + (unsigned)(t2_ringbase<BY>() - T2_ROWB);                          // ... (fp64: the ring is sa + constant)
+    else c.sr = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(t2_ringbase<BY>() + ty * t2_rrowb<T>() + (t2_rskip<T>() + tx * T2_V) * (int)sizeof(T));
 
     // ---- roles ---------------------------------------------------------------------------------------------
     {
@@ -468,11 +512,11 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     c.j_ijB = c.j_ijA && c.out;
 
     // ---- register sets (rotating roles, see t2_plane) ----------------------------------------------------------
-    T eA[3][V], eB[3][V], eC[3][V], bA[3][V], bB[3][V], bC[3][V];
+    double eA[3][V], eB[3][V], eC[3][V], bA[3][V], bB[3][V], bC[3][V];
 #pragma unroll
     for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int v = 0; v < V; ++v) { eA[q][v] = eB[q][v] = eC[q][v] = (T)0; bA[q][v] = bB[q][v] = bC[q][v] = (T)0; }
+        for (int v = 0; v < V; ++v) { eA[q][v] = eB[q][v] = eC[q][v] = 0.0; bA[q][v] = bB[q][v] = bC[q][v] = 0.0; }
 
     // ---- prologue: the first two ring slots, old E(kb-2) and its rows ------------------------------------------------
     const int k_first = c.kb - 2;
@@ -480,7 +524,7 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
         const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
         if (c.producer) {
 #pragma unroll
-            for (int d = 0; d < T2_D; ++d) mbar_init(smem0 + (unsigned)(t2_mbar0<BY>() + 8 * d), 1);
+            for (int d = 0; d < T2_D; ++d) mbar_init(smem0 + (unsigned)(t2_mbar0<T, BY>() + 8 * d), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             t2_issue_slot_tma<T, BY, 0>(a, smem0, c.tile_x, c.tile_y, k_first);
@@ -494,9 +538,9 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     }
     if (c.ldE) {
         const long long p0 = t2_plane_of(a, k_first) + c.roff;
-        ldg_vec<T, V>(a.Ein[0] + p0, eB[0]);
-        ldg_vec<T, V>(a.Ein[1] + p0, eB[1]);
-        ldg_vec<T, V>(a.Ein[2] + p0, eB[2]);
+        t2_ldg(a.Ein[0] + p0, eB[0]);
+        t2_ldg(a.Ein[1] + p0, eB[1]);
+        t2_ldg(a.Ein[2] + p0, eB[2]);
     }
     IO::template st<t2_xq<BY>(0)>(c.sa, eB[2]);
     IO::template st<t2_xq<BY>(1)>(c.sa, eB[0]);
@@ -523,7 +567,7 @@ __device__ __forceinline__ bool t2_meets(int lo, int hi, int blo, int bhi, int N
 
 template <typename T, int BY, int MINB, bool TWO_A, int ABL = 0>
 __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const __grid_constant__ FusedT2Args<T> a) {
-    constexpr int V = VecOf<T>::V;
+    constexpr int V = T2_V;
     // CTA-uniform: only the few tiles whose footprint (halo included) meets the box where J may be non-zero run
     // the loop that knows about currents; tiles that need no periodic wrap in i / j load through TMA.
     int tbx, tby;
