@@ -135,8 +135,11 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
         const bool fringe = (a.ib_lo[0] != s->main_lo[0]) || (a.ib_hi[0] != s->main_hi[0]);
         if (is_B && !do_pml && !fringe) return FDTD_OK;   // deferred half step: nothing left outside the inner box
     }
-    if (is_B) sweep_B_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
-    else sweep_E_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
+    // the PML = true instantiation: 2 cells per thread for float storage (see sweep_kernels.cuh)
+    constexpr int VP = (sizeof(T) == 4) ? 2 : V;
+    const dim3 grid_p((s->g.Ni + SWEEP_BX * VP - 1) / (SWEEP_BX * VP), gy, gz);
+    if (is_B) sweep_B_kernel<T, true, VP><<<grid_p, block, 0, s->stream>>>(a);
+    else sweep_E_kernel<T, true, VP><<<grid_p, block, 0, s->stream>>>(a);
     FDTD_CUDA_TRY(cudaGetLastError());
     s->launches++;
     return FDTD_OK;
@@ -167,12 +170,13 @@ static fdtd_status_t launch_rim_sweep(Solver* s, bool is_B, int n_half, const in
         }
     }
     dim3 block(SWEEP_BX, SWEEP_BY);
-    const int gx = (s->g.Ni + SWEEP_BX * V - 1) / (SWEEP_BX * V);
+    constexpr int VP = (sizeof(T) == 4) ? 2 : V;
+    const int gx = (s->g.Ni + SWEEP_BX * VP - 1) / (SWEEP_BX * VP);
     const int gy = (s->g.Nj + SWEEP_BY - 1) / SWEEP_BY;
     a.kc = pick_kc(s, gx * gy, s->g.nk);
     dim3 grid(gx, gy, (s->g.nk + a.kc - 1) / a.kc);
-    if (is_B) sweep_B_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
-    else sweep_E_kernel<T, true><<<grid, block, 0, s->stream>>>(a);
+    if (is_B) sweep_B_kernel<T, true, VP><<<grid, block, 0, s->stream>>>(a);
+    else sweep_E_kernel<T, true, VP><<<grid, block, 0, s->stream>>>(a);
     FDTD_CUDA_TRY(cudaGetLastError());
     s->launches++;
     return FDTD_OK;

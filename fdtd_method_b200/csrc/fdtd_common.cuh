@@ -85,6 +85,10 @@ __device__ __forceinline__ void ldv(const float* p, double (&o)[4]) {
     const float4 v = *reinterpret_cast<const float4*>(p);
     o[0] = (double)v.x; o[1] = (double)v.y; o[2] = (double)v.z; o[3] = (double)v.w;
 }
+__device__ __forceinline__ void ldv(const float* p, double (&o)[2]) {   // 2 cells per thread (float PML sweeps)
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    o[0] = (double)v.x; o[1] = (double)v.y;
+}
 __device__ __forceinline__ double lds1(const double* p) { return *p; }
 __device__ __forceinline__ double lds1(const float* p) { return (double)*p; }
 
@@ -92,6 +96,10 @@ __device__ __forceinline__ double lds1(const float* p) { return (double)*p; }
 __device__ __forceinline__ void stv(double* p, const double (&v)[2], int nvalid) {
     if (nvalid >= 2) *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
     else if (nvalid == 1) p[0] = v[0];
+}
+__device__ __forceinline__ void stv(float* p, const double (&v)[2], int nvalid) {
+    if (nvalid >= 2) *reinterpret_cast<float2*>(p) = make_float2((float)v[0], (float)v[1]);
+    else if (nvalid == 1) p[0] = (float)v[0];
 }
 __device__ __forceinline__ void stv(float* p, const double (&v)[4], int nvalid) {
     if (nvalid >= 4) {

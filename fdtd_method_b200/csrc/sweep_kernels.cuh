@@ -54,9 +54,11 @@ struct SweepArgs {
 constexpr int SWEEP_BX = 32;  // lanes along i
 constexpr int SWEEP_BY = 8;   // rows along j
 
-template <typename T, bool PML>
+// V = cells per thread: 16 bytes' worth by default; the float PML instantiation takes 2 (8-byte accesses, still whole
+// 32-byte sectors per 4 lanes) -- with 4 cells of double arithmetic plus split fields it needs 194-224 registers and
+// runs one CTA per SM.
+template <typename T, bool PML, int V = VecOf<T>::V>
 __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const SweepArgs<T> a) {
-    constexpr int V = VecOf<T>::V;
     const int Ni = a.g.Ni, Nj = a.g.Nj;
     const int i0 = (blockIdx.x * SWEEP_BX + threadIdx.x) * V;
     const int j = blockIdx.y * SWEEP_BY + threadIdx.y;
@@ -228,9 +230,8 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
     }
 }
 
-template <typename T, bool PML>
+template <typename T, bool PML, int V = VecOf<T>::V>
 __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const SweepArgs<T> a) {
-    constexpr int V = VecOf<T>::V;
     const int Ni = a.g.Ni, Nj = a.g.Nj;
     const int i0 = (blockIdx.x * SWEEP_BX + threadIdx.x) * V;
     const int j = blockIdx.y * SWEEP_BY + threadIdx.y;
