@@ -47,6 +47,25 @@ def halo_plan(nk_local: int, fused: bool) -> List[PlaneMove]:
             [PlaneMove(c, top, -1, +1) for c in (BX, BY)])
 
 
+JX, JY, JZ = int(Component.JX), int(Component.JY), int(Component.JZ)
+
+
+def halo_plan_t2(nk_local: int) -> List[PlaneMove]:
+    """Planes one rank SENDS before a two-step (T2) pass -- the plan csrc/fdtd_capi.cu::exchange_t2 executes.
+    ``dst_ghost`` is the receiver's ghost plane: -2, -1 below plane 0; +1, +2 = planes nk, nk+1.
+
+    to rank+1: E, B planes nk-1 and nk-2 -> its ghosts -1 and -2 (it rebuilds B1(-2), B1(-1), E1(-1) itself), and
+               J plane nk-1 -> ghost -1 (E1(-1) contains the current term);
+    to rank-1: E, B, J plane 0 -> its ghost +1 (it rebuilds B1(nk), E1(nk)), and Ex, Ey plane 1 -> ghost +2
+               (B1(nk) reads E(nk+1))."""
+    nk = nk_local
+    up = [PlaneMove(c, nk - d, -d, +1) for c in (EX, EY, EZ, BX, BY, BZ) for d in (1, 2)]
+    up += [PlaneMove(c, nk - 1, -1, +1) for c in (JX, JY, JZ)]
+    down = [PlaneMove(c, 0, +1, -1) for c in (EX, EY, EZ, BX, BY, BZ, JX, JY, JZ)]
+    down += [PlaneMove(c, 1, +2, -1) for c in (EX, EY)]
+    return up + down
+
+
 def create_distributed(cls, parameters, dt, *args, group=None, **kw):
     """Construct one slab solver per torch.distributed rank (``cls`` = FDTD or FDTD_PML) and initialise the
     NCCL ring: rank 0 creates the unique id, torch.distributed broadcasts it."""
