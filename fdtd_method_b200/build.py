@@ -18,7 +18,8 @@ NVCC_FLAGS = [
     "-fmad=false",                 # belt and braces: arithmetic already uses __dadd_rn/__dmul_rn (no contraction)
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
-] + (["-DFDTD_T2_ABLATE"] if os.environ.get("FDTD_T2_ABLATE") else [])
+] + (["-DFDTD_T2_ABLATE"] if os.environ.get("FDTD_T2_ABLATE") else []) \
+  + (["-DFDTD_T2_F32_MAGIC=" + os.environ["FDTD_T2_F32_MAGIC"]] if os.environ.get("FDTD_T2_F32_MAGIC") else [])
 
 
 def nvcc() -> str:

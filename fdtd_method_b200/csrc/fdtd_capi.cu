@@ -387,9 +387,13 @@ static bool encode_tmap(const Solver* s, CUtensorMap* tm, int comp, int gen, int
     const cuuint32_t box[3] = {(cuuint32_t)(s->esz == 8 ? t2_rbox<double>() : t2_rbox<float>()), (cuuint32_t)by, 1u};   // 64 cells = 512 B (fp64) / 68 cells = 272 B (fp32)
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (box[0] > (cuuint32_t)s->g.Ni || by > s->g.Nj) return false;   // no wrap-free tile exists anyway
+    static int promo = -1;   // FDTD_B200_TMA_L2 = 0 none, 64, 128, 256 (default; measured, profiles/tma_l2_r01.jsonl)
+    if (promo < 0) { const char* e = std::getenv("FDTD_B200_TMA_L2"); promo = e ? std::atoi(e) : 256; }
+    const CUtensorMapL2promotion l2 = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     const CUresult r = enc(tm, s->esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                            s->base[comp][gen], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 

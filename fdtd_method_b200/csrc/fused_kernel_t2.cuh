@@ -178,6 +178,26 @@ template <bool CS> __device__ __forceinline__ void t2_stg(float* p, const double
 
 // B += n_half * h(E)   (FDTD.cpp:121-126).  e = E(k), ek = E(k+1), (ezu, exu) = Ez, Ex one row up,
 // (ez_nl, ey_nl) = Ez, Ey first element of the next lane.
+// Round a double to the nearest float (ties to even), result kept as a double.  MAGIC: for x in the binade 2^E the
+// constant M = 1.5 * 2^(E + 29) has ulp(M) = 2^(E - 23) = the float spacing there, so x + M is x rounded to that spacing
+// by the adder (ties to even: M / ulp is even) and subtracting M is exact.  Float denormals: E clamped to -126.  Anything
+// at or above 2^127 (overflow to inf, NaN) takes the conversion path.  Two DADD + a few integer ops on the high word
+// instead of two F2F (which run at 16 per clock per SM).
+#ifndef FDTD_T2_F32_MAGIC
+#define FDTD_T2_F32_MAGIC 0   // build-time switch (fdtd_method_b200/build.py: FDTD_T2_F32_MAGIC=1 in the environment)
+#endif
+template <typename T>
+__device__ __forceinline__ double t2_round(double x) {
+    if (sizeof(T) == 8) return x;
+    if (!FDTD_T2_F32_MAGIC) return (double)__double2float_rn(x);
+    const int hi = __double2hiint(x);
+    int e = (hi >> 20) & 0x7ff;
+    if (e >= 1023 + 127) return (double)__double2float_rn(x);
+    e = max(e, 1023 - 126);
+    const double M = __hiloint2double(((e + 29) << 20) | 0x00080000, 0);
+    return __dsub_rn(__dadd_rn(x, M), M);
+}
+
 template <typename T>
 __device__ __forceinline__ void t2_update_B(double (&b)[3][T2_V], const double (&e)[3][T2_V], const double (&ek)[3][T2_V],
                                             const double (&ezu)[T2_V], const double (&exu)[T2_V], const double ez_nl,
@@ -192,13 +212,13 @@ __device__ __forceinline__ void t2_update_B(double (&b)[3][T2_V], const double (
         const double hx = dsub(dmul(cBz, dsub(ek[1][q], ey)), dmul(cBy, dsub(ezu[q], ez)));
         const double hy = dsub(dmul(cBx, dsub(ezr, ez)), dmul(cBz, dsub(ek[0][q], ex)));
         const double hz = dsub(dmul(cBy, dsub(exu[q], ex)), dmul(cBx, dsub(eyr, ey)));
-        double nbx = round_store<T>(dadd(b[0][q], hx));
-        double nby = round_store<T>(dadd(b[1][q], hy));
-        double nbz = round_store<T>(dadd(b[2][q], hz));
+        double nbx = t2_round<T>(dadd(b[0][q], hx));
+        double nby = t2_round<T>(dadd(b[1][q], hy));
+        double nbz = t2_round<T>(dadd(b[2][q], hz));
         if (two) {
-            nbx = round_store<T>(dadd(nbx, hx));
-            nby = round_store<T>(dadd(nby, hy));
-            nbz = round_store<T>(dadd(nbz, hz));
+            nbx = t2_round<T>(dadd(nbx, hx));
+            nby = t2_round<T>(dadd(nby, hy));
+            nbz = t2_round<T>(dadd(nbz, hz));
         }
         b[0][q] = nbx; b[1][q] = nby; b[2][q] = nbz;
     }
@@ -225,9 +245,9 @@ __device__ __forceinline__ void t2_update_E(double (&e)[3][T2_V], const double (
             ty_ = dadd(dmul(cJ, jv[1][q]), ty_);
             tz_ = dadd(dmul(cJ, jv[2][q]), tz_);
         }
-        e[0][q] = round_store<T>(dadd(e[0][q], dsub(tx_, dmul(cEz, dsub(by, byk[q])))));
-        e[1][q] = round_store<T>(dadd(e[1][q], dsub(ty_, dmul(cEx, dsub(bz, bzl)))));
-        e[2][q] = round_store<T>(dadd(e[2][q], dsub(tz_, dmul(cEy, dsub(bx, bxd[q])))));
+        e[0][q] = t2_round<T>(dadd(e[0][q], dsub(tx_, dmul(cEz, dsub(by, byk[q])))));
+        e[1][q] = t2_round<T>(dadd(e[1][q], dsub(ty_, dmul(cEx, dsub(bz, bzl)))));
+        e[2][q] = t2_round<T>(dadd(e[2][q], dsub(tz_, dmul(cEy, dsub(bx, bxd[q])))));
     }
 }
 
@@ -429,7 +449,7 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
                     for (int q = 0; q < V; ++q) {
                         const int ii = c.i + q;
                         if (ii >= a.s_lo[0] && ii < a.s_hi[0]) {
-                            const double v = round_store<T>(dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wy), wz));
+                            const double v = t2_round<T>(dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wy), wz));
                             jv[0][q] = v; jv[1][q] = v; jv[2][q] = v;
                         }
                     }
