@@ -47,6 +47,8 @@ def main():
     variants = [("3 streams H=2 (default)", 0), ("3 streams H=4", 4 << 8), ("boundary after interior H=2", 4),
                 ("boundary after interior H=4 (previous default)", 4 | (4 << 8)), ("no overlap", 1),
                 ("3 streams, exchange skipped", 2), ("single launch, exchange skipped", 3)]
+    if os.environ.get("PROBE_FIRST_ONLY"):
+        variants = variants[:1]
     for name, dbg in variants:
         os.environ["FDTD_B200_MGPU_DEBUG"] = str(dbg)
         best = None
