@@ -237,8 +237,17 @@ def run_ours(a):
     cells_total = n * n * Nk
 
     # synthetic inputs in pinned host memory (also the e2e leg's H2D source)
-    host = [torch.empty((nk_local, n, n), dtype=torch.float64 if a.dtype == "f64" else torch.float32).pin_memory()
-            for _ in range(6)]
+    tdt = torch.float64 if a.dtype == "f64" else torch.float32
+    host, pinned = [], True
+    for _ in range(6):
+        t = torch.empty((nk_local, n, n), dtype=tdt)
+        if pinned:
+            try:
+                t = t.pin_memory()
+            except Exception as e:      # 6 x field per rank (48 GiB at 8 x 512^3 fp64): fall back to pageable rather than lose the run
+                pinned = False
+                print(f"bench.py: rank {rank}: pin_memory failed ({e!r}); the e2e leg uses pageable host buffers", file=sys.stderr)
+        host.append(t)
     rng = np.random.default_rng(42 + rank)
     for t in host:
         v = t.numpy()
@@ -363,7 +372,7 @@ def run_ours(a):
             "config": workload_config(a, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": f"upload 6 fields from pinned host + {e2e_steps} x (scatter J from host, update_fields, gather "
+                    "what": f"upload 6 fields from {'pinned' if pinned else 'PAGEABLE (pin_memory failed)'} host + {e2e_steps} x (scatter J from host, update_fields, gather "
                             f"10x10 Ex probe to host) + download 6 fields, wall clock, max over ranks", "probe_checksum": probe_sum},
             "gpu_launches": launches,
             "roofline": roof,
