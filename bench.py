@@ -119,6 +119,11 @@ def cpu_solver(shape, pml):
     from oracle import pyoracle
     Ni, Nj, Nk = shape
     if pyoracle.have_reference():
+        # all the host threads: torchrun exports OMP_NUM_THREADS=1 to its children, which would silently make this a
+        # single-thread baseline at N > 1
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        if pyoracle.Reference.max_threads() < ncpu:
+            pyoracle.Reference.set_threads(ncpu)
         return pyoracle.Reference(Ni, Nj, Nk, C, C, C, 0.2, pml_percent=pml), "reference", pyoracle.Reference.max_threads()
     return pyoracle.Oracle(Ni, Nj, Nk, C, C, C, 0.2, pml_percent=pml), "port", (os.cpu_count() or 1)
 
