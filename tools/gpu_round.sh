@@ -1,20 +1,84 @@
 #!/bin/bash
-# One gpurun call that refreshes the round's evidence: GPU parity suite, bench (both arms), BASELINE config table,
-# ncu launch list and one `ncu --set full` capture of the dominant kernel.  Output under gpurun_out/<tag>/.
-tag=${1:-r01}
-out=gpurun_out/$tag
-mkdir -p $out
-nvidia-smi -L > $out/gpu.txt
-nproc >> $out/gpu.txt
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > $out/pytest_gpu.log 2>&1
-tail -3 $out/pytest_gpu.log
-timeout 600 python bench.py --steps 200 --warmup 10 > $out/bench_n1.json 2> $out/bench_n1.err
-cat $out/bench_n1.json
-timeout 400 python bench.py --impl reference --steps 20 --warmup 3 > $out/bench_ref.json 2> $out/bench_ref.err
-timeout 900 python tools/config_table.py > $out/config_table.jsonl 2> $out/config_table.err
-cat $out/config_table.jsonl
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
-    python bench.py --steps 20 --warmup 3 --no-cpu > $out/bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_BE_T2 -s 4 -c 1 -f -o $out/t2_full \
-    python bench.py --steps 12 --warmup 3 --no-cpu > $out/ncu_full.log 2>&1
-ls -la $out
+# One entry point for every GPU-box run of a round.  EVERY command runs under `timeout` (a hung NCCL experiment once
+# ate the rest of a round's GPU budget).  Usage (from the repo root, normally through gpurun):
+#
+#     bash tools/gpu_round.sh <tag> <stage> [<stage> ...]          output under gpurun_out/<tag>/
+#
+# 1-GPU stages
+#   tests        GPU parity suite (pytest -m gpu) + __graft_entry__.smoke()
+#   bench        bench.py (ours) and bench.py --impl reference
+#   table        tools/config_table.py (BASELINE configs on one GPU)
+#   launches     ncu launch list (gpu__time_duration.sum) of the bench command
+#   ncu          ncu --set full of the T2 pass, fp64 and fp32
+#   pml          PML launch list with DRAM bytes + ncu --set full of the sweeps + PML bench line
+#   e2e          tools/e2e_breakdown.py
+#   kc           DRAM traffic / duration of the T2 pass vs chunk length (512^3 and 1024^3)
+# N-GPU stages (set NGPU=2|4|8 and call gpurun --gpus $NGPU)
+#   mtests       tests/test_multi_gpu.py
+#   mbench       weak-scaling bench at $NGPU, PML bench at $NGPU, 1024^3 strong scaling at $NGPU, 1-GPU bench on the same box
+#   mprobe       tools/mgpu_probe.py (stream-structure variants)
+tag=${1:?tag}; shift
+out=gpurun_out/$tag; mkdir -p $out
+N=${NGPU:-2}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+nvidia-smi -L > $out/gpu.txt 2>&1; nproc >> $out/gpu.txt
+
+ncu_rows() {   # csv -> one json line per launch: duration + dram bytes
+python - "$@" <<'PY'
+import csv, sys
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5 and r[0].isdigit()]
+d = {}
+for r in rows:
+    d.setdefault(r[0], {"kernel": r[4] if len(r) > 4 else ""})[r[-3]] = float(r[-1].replace(",", ""))
+for k, v in d.items():
+    rd, wr, t = v.get("dram__bytes_read.sum", 0), v.get("dram__bytes_write.sum", 0), v.get("gpu__time_duration.sum", 0)
+    print('{"id": %s, "ms": %.3f, "read_GB": %.2f, "write_GB": %.2f, "GBs": %.0f, "tag": "%s"}' % (k, t / 1e6, rd / 1e9, wr / 1e9, (rd + wr) / max(t, 1), " ".join(sys.argv[2:])))
+PY
+}
+
+for stage in "$@"; do
+case $stage in
+tests)
+  ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $out/pytest_gpu.log 2>&1; tail -3 $out/pytest_gpu.log
+  timeout 300 python __graft_entry__.py --smoke > $out/smoke.log 2>&1; tail -2 $out/smoke.log ;;
+bench)
+  timeout 600 python bench.py --steps 200 --warmup 10 > $out/bench_n1.json 2> $out/bench_n1.err; cut -c1-300 $out/bench_n1.json
+  timeout 400 python bench.py --impl reference --steps 20 --warmup 3 > $out/bench_ref.json 2> $out/bench_ref.err; cut -c1-200 $out/bench_ref.json ;;
+table)
+  timeout 900 python tools/config_table.py > $out/config_table.jsonl 2> $out/config_table.err; cut -c1-220 $out/config_table.jsonl ;;
+launches)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
+      python bench.py --steps 20 --warmup 3 --no-cpu > $out/bench_under_ncu.log 2>&1 ;;
+ncu)
+  for dt in f64 f32; do
+    timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_BE_T2 -s 4 -c 1 -f -o $out/t2_${dt}_full \
+        python bench.py --dtype $dt --steps 12 --warmup 3 --no-cpu --no-e2e > $out/ncu_$dt.log 2>&1
+  done ;;
+pml)
+  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file $out/launches_pml.csv \
+      python bench.py --workload pml --steps 4 --warmup 3 --no-cpu --no-e2e > $out/bench_pml_under_ncu.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:sweep_ -s 12 -c 4 -f -o $out/pml_full \
+      python bench.py --workload pml --steps 4 --warmup 3 --no-cpu --no-e2e > $out/ncu_pml_full.log 2>&1
+  timeout 600 python bench.py --workload pml --steps 100 --warmup 10 --no-cpu > $out/bench_pml.json 2> $out/bench_pml.err; cut -c1-300 $out/bench_pml.json ;;
+e2e)
+  timeout 300 python tools/e2e_breakdown.py --steps 60 > $out/e2e_breakdown.json 2> $out/e2e_breakdown.err; cat $out/e2e_breakdown.json ;;
+kc)
+  for cfg in "512 32" "512 64" "512 171" "1024 32" "1024 64" "1024 128" "1024 512"; do
+    read n kc <<< "$cfg"
+    timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:fused_BE_T2 -s 2 -c 1 --csv \
+        --log-file $out/kc_${n}_$kc.csv python tools/sweep.py --n $n --no-sweeps --t2 0 --kc $kc --steps 6 > /dev/null 2>&1
+    ncu_rows $out/kc_${n}_$kc.csv n=$n kc=$kc
+  done | tee $out/kc_traffic.jsonl ;;
+mtests)
+  ( time timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > $out/pytest_mgpu.log 2>&1; tail -4 $out/pytest_mgpu.log | cut -c1-300 ;;
+mbench)
+  timeout 600 $TR --master-port 29521 bench.py --gpus $N --steps 200 --warmup 10 > $out/bench_n$N.json 2> $out/bench_n$N.err; cut -c1-300 $out/bench_n$N.json
+  timeout 600 $TR --master-port 29522 bench.py --gpus $N --steps 100 --warmup 10 --workload pml --no-e2e > $out/bench_pml_n$N.json 2> $out/bench_pml_n$N.err; cut -c1-300 $out/bench_pml_n$N.json
+  timeout 600 $TR --master-port 29523 bench.py --gpus $N --steps 100 --warmup 10 --size 1024 --scaling strong --no-e2e > $out/bench_strong1024_n$N.json 2> $out/bench_strong1024_n$N.err; cut -c1-300 $out/bench_strong1024_n$N.json
+  timeout 600 python bench.py --steps 200 --warmup 10 --no-cpu --no-e2e > $out/bench_n1_samebox.json 2> $out/bench_n1_samebox.err; cut -c1-300 $out/bench_n1_samebox.json ;;
+mprobe)
+  timeout 600 $TR --master-port 29511 tools/mgpu_probe.py > $out/mgpu_probe.log 2>&1; grep variant $out/mgpu_probe.log ;;
+*) echo "unknown stage $stage" ;;
+esac
+done
+ls -la $out | tail -n +2 | head -40
