@@ -39,7 +39,7 @@ class Info(ctypes.Structure):
                 ("launches", ctypes.c_int64), ("steps_done", ctypes.c_int64),
                 ("fused", ctypes.c_int32), ("rank", ctypes.c_int32), ("nranks", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("temporal", ctypes.c_int32), ("passes_t2", ctypes.c_int64),
-                ("kernel_ns", ctypes.c_int64)]
+                ("kernel_ns", ctypes.c_int64), ("transport", ctypes.c_int32), ("halo_in_kernel", ctypes.c_int32)]
 
 
 # every entry point include/fdtd_b200.h declares: name -> (restype, argtypes)
@@ -70,6 +70,9 @@ SIGNATURES = {
     "fdtd_get_stream": (_i, [_vp, ctypes.POINTER(_vp)]),
     "fdtd_nccl_unique_id": (_i, [_vp, _sz]),
     "fdtd_comm_init": (_i, [_vp, _vp, _sz]),
+    "fdtd_comm_init_local": (_i, [ctypes.POINTER(_vp), _i]),
+    "fdtd_timeline_enable": (_i, [_vp, _i]),
+    "fdtd_timeline_read": (_i, [_vp, _pd, _i, _pi]),
     "fdtd_slab_range": (None, [_i, _i, _i, _pi, _pi]),
     "fdtd_pml_profile": (_i, [_i, _i, _d, _d, _pd, _pd, _pd]),
     "fdtd_pml_thickness": (_i, [_i, _d]),

@@ -9,7 +9,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libfdtd_b200.so")
-SOURCES = ["fdtd_capi.cu", "nccl_ring.cu"]
+SOURCES = ["fdtd_capi.cu", "nccl_ring.cu", "peer_ring.cu"]
 HEADERS = ["fdtd_common.cuh", "sweep_kernels.cuh", "fused_kernel.cuh", "fused_kernel_v2.cuh", "fused_kernel_t2.cuh", "solver.h", os.path.join("..", "..", "include", "fdtd_b200.h")]
 
 NVCC_FLAGS = [

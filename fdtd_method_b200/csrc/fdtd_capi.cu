@@ -182,18 +182,26 @@ static fdtd_status_t launch_rim_sweep(Solver* s, bool is_B, int n_half, const in
     return FDTD_OK;
 }
 
-// Variant table of the fused pass (BY warps x RJ rows per warp); FDTD_B200_FUSED_VARIANT picks one.
-// (read on every launch so that tools/sweep.py can walk the table inside one process)
-static int fused_variant() {
-    const char* e = std::getenv("FDTD_B200_FUSED_VARIANT");
-    int v = e ? std::atoi(e) : -1;
-    if (v > 40) v = -1;
-    return v;   // -1: per-dtype default
+// Environment switches are read once per solver (Tunables, solver.h).
+static int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
 }
-static int fused_kc_override() {
-    const char* e = std::getenv("FDTD_B200_FUSED_KC");
-    return e ? std::atoi(e) : 0;
+static void read_tunables(Tunables& t) {
+    t.fused_variant = env_int("FDTD_B200_FUSED_VARIANT", -1);
+    t.fused_kc = env_int("FDTD_B200_FUSED_KC", 0);
+    t.t2_variant = env_int("FDTD_B200_T2_VARIANT", 0);
+    t.t2_strip = env_int("FDTD_B200_T2_STRIP", 0);
+    t.st_cs = env_int("FDTD_B200_ST_CS", 1);
+    t.tma_l2 = env_int("FDTD_B200_TMA_L2", 256);
+    t.no_tma = env_int("FDTD_B200_NO_TMA", 0) != 0;
+    t.no_t2 = env_int("FDTD_B200_NO_T2", 0) != 0;
+    t.no_lazy = env_int("FDTD_B200_NO_LAZY", 0) != 0;
+    t.mgpu_debug = env_int("FDTD_B200_MGPU_DEBUG", 0);
+    t.pml_t2_f32 = env_int("FDTD_B200_PML_T2_F32", 0) != 0;
 }
+// one cudaFuncSetAttribute per kernel family and solver (bit in Solver::configured)
+enum { CFG_FUSED2 = 0, CFG_T2 = 8 };
 
 template <typename T, int BY, int RJ, int MINB>
 static cudaError_t launch_fused_variant(Solver* s, FusedArgs<T>& a) {
@@ -203,7 +211,7 @@ static cudaError_t launch_fused_variant(Solver* s, FusedArgs<T>& a) {
     const int gx = (s->g.Ni + TIU - 1) / TIU;
     const int gy = (s->g.Nj + TJU - 1) / TJU;
     const int np = a.k_hi - a.k_lo;
-    int kc = fused_kc_override();
+    int kc = s->tun.fused_kc;
     if (kc <= 0) {
         kc = 64;
         while (kc > 8 && (long long)gx * gy * ((np + kc - 1) / kc) < 148 * 6) kc /= 2;
@@ -216,21 +224,20 @@ static cudaError_t launch_fused_variant(Solver* s, FusedArgs<T>& a) {
 }
 
 template <typename T, int BY, int PF, int D, int MINB>
-static cudaError_t launch_fused2_variant(Solver* s, FusedArgs<T>& a) {
+static cudaError_t launch_fused2_variant(Solver* s, FusedArgs<T>& a, int cfg_bit) {
     constexpr int V = VecOf<T>::V;
     constexpr int TIU = FUSED_OUT_LANES * V;
     constexpr int TJU = BY - 2;
     constexpr size_t smem = fused2_smem_bytes<BY, PF, D>();
-    static bool configured[16] = {};
-    if (!configured[s->device & 15]) {
+    if (!(s->configured & (1u << cfg_bit))) {
         cudaError_t e = cudaFuncSetAttribute(fused_BE2_kernel<T, BY, PF, D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[s->device & 15] = true;
+        s->configured |= (1u << cfg_bit);
     }
     const int gx = (s->g.Ni + TIU - 1) / TIU;
     const int gy = (s->g.Nj + TJU - 1) / TJU;
     const int np = a.k_hi - a.k_lo;
-    int kc = fused_kc_override();
+    int kc = s->tun.fused_kc;
     if (kc <= 0) {
         kc = 64;
         while (kc > 8 && (long long)gx * gy * ((np + kc - 1) / kc) < 148 * 6) kc /= 2;
@@ -256,34 +263,17 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
     a.k_lo = k_lo; a.k_hi = k_hi; a.n_half = n_half;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     cudaError_t e;
-    int variant = fused_variant();
-    if (variant < 0) variant = (sizeof(T) == 8) ? 28 : 0;  // measured best on B200 (profiles/sweep_t2_r01.md, profiles/t1_variants_r01.jsonl: v28 2.34 ms, v5 2.42 ms)
+    // Variants kept after the round-1 sweeps (profiles/sweep_t2_r01.md, profiles/t1_variants_r01.jsonl): fp64 default
+    // v28 = 16 rows, register prefetch, 1 CTA/SM (2.34 ms at 512^3); fp32 default v0 = 8 rows, 2 CTAs/SM; v5 = 8 rows,
+    // 3 CTAs/SM (2.42 ms, the round-1 first default); v21 = its register-prefetch twin.
+    int variant = s->tun.fused_variant;
+    if (variant < 0) variant = (sizeof(T) == 8) ? 28 : 0;
     switch (variant) {
         default:
         case 0: e = launch_fused_variant<T, 8, 1, 2>(s, a); break;
-        case 1: e = launch_fused_variant<T, 12, 1, 1>(s, a); break;
-        case 2: e = launch_fused_variant<T, 8, 2, 1>(s, a); break;
-        case 3: e = launch_fused_variant<T, 4, 2, 2>(s, a); break;
-        case 4: e = launch_fused_variant<T, 10, 1, 2>(s, a); break;
         case 5: e = launch_fused_variant<T, 8, 1, 3>(s, a); break;
-        case 6: e = launch_fused_variant<T, 8, 1, 4>(s, a); break;
-        case 7: e = launch_fused_variant<T, 4, 1, 6>(s, a); break;
-        case 8: e = launch_fused_variant<T, 4, 1, 8>(s, a); break;
-        case 9: e = launch_fused_variant<T, 10, 1, 3>(s, a); break;
-        case 10: e = launch_fused_variant<T, 6, 1, 4>(s, a); break;
-        case 11: e = launch_fused_variant<T, 6, 1, 5>(s, a); break;
-        // v2: <BY, PF (1 = register prefetch, 2 = cp.async ring), ring depth, min CTAs/SM>
-        case 20: e = launch_fused2_variant<T, 8, 1, 1, 2>(s, a); break;
-        case 21: e = launch_fused2_variant<T, 8, 1, 1, 3>(s, a); break;
-        case 22: e = launch_fused2_variant<T, 8, 2, 2, 2>(s, a); break;
-        case 23: e = launch_fused2_variant<T, 8, 2, 3, 2>(s, a); break;
-        case 24: e = launch_fused2_variant<T, 10, 2, 2, 2>(s, a); break;
-        case 25: e = launch_fused2_variant<T, 16, 2, 2, 1>(s, a); break;
-        case 26: e = launch_fused2_variant<T, 12, 2, 3, 1>(s, a); break;
-        case 27: e = launch_fused2_variant<T, 8, 0, 1, 3>(s, a); break;
-        case 28: e = launch_fused2_variant<T, 16, 1, 1, 1>(s, a); break;
-        case 29: e = launch_fused2_variant<T, 12, 1, 1, 2>(s, a); break;
-        case 30: e = launch_fused2_variant<T, 8, 2, 4, 1>(s, a); break;
+        case 21: e = launch_fused2_variant<T, 8, 1, 1, 3>(s, a, CFG_FUSED2 + 0); break;
+        case 28: e = launch_fused2_variant<T, 16, 1, 1, 1>(s, a, CFG_FUSED2 + 1); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "fused_BE_kernel launch");
     s->launches++;
@@ -292,28 +282,22 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
 
 // ---- temporally blocked pass: two Yee steps per launch (fused_kernel_t2.cuh) -------------------------------
 // Variant table <BY rows per CTA, min CTAs/SM>; FDTD_B200_T2_VARIANT picks one.
-static int t2_variant() {
-    const char* e = std::getenv("FDTD_B200_T2_VARIANT");
-    return e ? std::atoi(e) : -1;
-}
-
 template <typename T, int BY, int MINB, int ABL = 0>
-static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
+static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, int cfg_bit) {
     constexpr int V = T2_V;   // 2 cells per lane for both storage types
     constexpr int TIU = FUSED_OUT_LANES * V;
     constexpr int TJU = BY - 4;
     constexpr size_t smem = fused_t2_smem_bytes<T, BY>();
-    static bool configured[16] = {};
-    if (!configured[s->device & 15]) {
+    if (!(s->configured & (1u << cfg_bit))) {
         cudaError_t e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, MINB, true, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, MINB, false, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[s->device & 15] = true;
+        s->configured |= (1u << cfg_bit);
     }
     const int gx = (s->g.Ni + TIU - 1) / TIU;
     const int gy = (s->g.Nj + TJU - 1) / TJU;
     const int np = a.k_hi - a.k_lo, np2 = a.k_hi2 - a.k_lo2;
-    int kc = fused_kc_override();
+    int kc = s->tun.fused_kc;
     if (kc <= 0) {
         // Chunk count m of the (first) plane range: every chunk costs 3 redundant plane iterations plus ~2 of start-up,
         // and the CTAs run in waves of one per SM, so minimise  waves(m) * (planes per chunk + 5)  -- long chunks, but
@@ -346,11 +330,14 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a) {
     const int gz = a.nz1 + (np2 + kc - 1) / kc;
     a.gx = gx; a.gy = gy;
     {
-        const char* e = std::getenv("FDTD_B200_T2_STRIP");   // tile columns per strip; >= gx = row-major ids
-        int w = e ? std::atoi(e) : gx;   // row-major: measured best (profiles/strip_r01.jsonl) -- a missed x-neighbour costs
-                                          // as much as a missed y-neighbour (whole 128-byte lines at both ends of a 512-byte row)
-        a.strip_w = w < 1 ? 1 : (w > gx ? gx : w);
+        // tile columns per strip; >= gx = row-major ids: measured best (profiles/strip_r01.jsonl) -- a missed x-neighbour
+        // costs as much as a missed y-neighbour (whole 128-byte lines at both ends of a 512-byte row)
+        const int w = s->tun.t2_strip > 0 ? s->tun.t2_strip : gx;
+        a.strip_w = w > gx ? gx : w;
     }
+    // Halo-dependent chunks last: with the chunk order 1, 2, ..., nz-1, 0 the CTAs that read ghost planes (top chunk at
+    // its end, bottom chunk at its start) are dispatched after the interior ones, when the pushed planes have long landed.
+    a.z_rot = (a.halo_flags != nullptr && np2 == 0 && a.nz1 > 1) ? 1 : 0;
     if (a.n_half == 2) fused_BE_T2_kernel<T, BY, MINB, true, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
     else fused_BE_T2_kernel<T, BY, MINB, false, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
     return cudaGetLastError();
@@ -361,34 +348,23 @@ typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static tmap_encode_fn tmap_encoder() {
-    static tmap_encode_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        const char* off = std::getenv("FDTD_B200_NO_TMA");
-        if (!(off && std::atoi(off) != 0)) {
-            void* p = nullptr;
-            cudaDriverEntryPointQueryResult q;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-                q == cudaDriverEntryPointSuccess)
-                fn = reinterpret_cast<tmap_encode_fn>(p);
-            cudaGetLastError();
-        }
-    }
-    return fn;
+    // (looked up per call: a handful of calls per solver lifetime, the maps themselves are cached in the Solver)
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<tmap_encode_fn>(p);
+    cudaGetLastError();
+    return nullptr;
 }
 
 // 3-D tensor map of one component array of generation `gen` (ghost planes included), box = {64 cells, by rows, 1 plane}.
-static bool encode_tmap(const Solver* s, CUtensorMap* tm, int comp, int gen, int by) {
-    tmap_encode_fn enc = tmap_encoder();
-    if (!enc) return false;
+static bool encode_tmap(const Solver* s, tmap_encode_fn enc, CUtensorMap* tm, int comp, int gen, int by) {
     const cuuint64_t dims[3] = {(cuuint64_t)s->g.Ni, (cuuint64_t)s->g.Nj, (cuuint64_t)(s->g.nk + 2 * GHOST_PLANES)};
     const cuuint64_t strides[2] = {(cuuint64_t)s->g.pitch * s->esz, (cuuint64_t)s->g.plane * s->esz};
     const cuuint32_t box[3] = {(cuuint32_t)(s->esz == 8 ? t2_rbox<double>() : t2_rbox<float>()), (cuuint32_t)by, 1u};   // 64 cells = 512 B (fp64) / 68 cells = 272 B (fp32)
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (box[0] > (cuuint32_t)s->g.Ni || by > s->g.Nj) return false;   // no wrap-free tile exists anyway
-    static int promo = -1;   // FDTD_B200_TMA_L2 = 0 none, 64, 128, 256 (default; measured, profiles/tma_l2_r01.jsonl)
-    if (promo < 0) { const char* e = std::getenv("FDTD_B200_TMA_L2"); promo = e ? std::atoi(e) : 256; }
+    const int promo = s->tun.tma_l2;   // FDTD_B200_TMA_L2 = 0 none, 64, 128, 256 (default; measured, profiles/tma_l2_r01.jsonl)
     const CUtensorMapL2promotion l2 = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                     : promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     const CUresult r = enc(tm, s->esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
@@ -397,10 +373,24 @@ static bool encode_tmap(const Solver* s, CUtensorMap* tm, int comp, int gen, int
     return r == CUDA_SUCCESS;
 }
 
+// The six maps of generation `gen` (box rows `by`): encoded on first use, then served from the solver's cache (the
+// arrays never move; round 1 re-encoded all six on every launch).
+static const CUtensorMap* cached_tmaps(Solver* s, int gen, int by) {
+    if (s->tun.no_tma) return nullptr;
+    if (s->tmaps_by[gen] != by) {
+        tmap_encode_fn enc = tmap_encoder();
+        bool ok = enc != nullptr;
+        for (int c = 0; c < 6 && ok; ++c) ok = encode_tmap(s, enc, &s->tmaps[gen][c], EX + c, gen, by);
+        if (!ok) { s->tmaps_by[gen] = -1; return nullptr; }
+        s->tmaps_by[gen] = by;
+    }
+    return s->tmaps[gen];
+}
+
 template <typename T>
-static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_lo2, int k_hi2, int src2, double amp2) {
+static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_lo2, int k_hi2, int src2, double amp2, unsigned halo_seq) {
     static const int by_of_variant[] = {16, 8, 12};
-    int variant = t2_variant();
+    int variant = s->tun.t2_variant;
     if (variant < 0 || (variant > 2 && variant < 11) || variant > 15) variant = 0;
     FusedT2Args<T> a;
     std::memset(&a, 0, sizeof(a));
@@ -420,22 +410,28 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
         a.sb_lo[d] = s->pml_t2 ? s->sb_lo[d] : 0;
         a.sb_hi[d] = s->pml_t2 ? s->sb_hi[d] : (d == 0 ? s->g.Ni : s->g.Nj);
     }
-    a.use_tma = 1;
-    { const char* e = std::getenv("FDTD_B200_ST_CS"); a.st_cs = e ? std::atoi(e) : 1; }   // profiles/stcs_r01.jsonl: DRAM reads -3 %, +1.5 %
+    a.st_cs = s->tun.st_cs;   // profiles/stcs_r01.jsonl: DRAM reads -3 %, +1.5 %
+    if (halo_seq) {            // the CTAs that read ghost planes wait for the neighbours' pushes themselves (peer_ring.cu)
+        a.halo_flags = peer_data_flags(s);
+        a.halo_err = peer_error_word(s);
+        a.halo_seq = halo_seq;
+    }
     const int by = variant < 3 ? by_of_variant[variant] : 16;
-    for (int c = 0; c < 3 && a.use_tma; ++c)
-        if (!encode_tmap(s, &a.tmE[c], EX + c, s->cur, by) || !encode_tmap(s, &a.tmB[c], BX + c, s->cur, by)) a.use_tma = 0;
+    if (const CUtensorMap* tm = cached_tmaps(s, s->cur, by)) {
+        a.use_tma = 1;
+        for (int c = 0; c < 3; ++c) { a.tmE[c] = tm[c]; a.tmB[c] = tm[3 + c]; }
+    }
     cudaError_t e;
     switch (variant) {
         default:
-        case 0: e = launch_t2_variant<T, 16, 1>(s, a); break;
-        case 1: e = launch_t2_variant<T, 8, 2>(s, a); break;
-        case 2: e = launch_t2_variant<T, 12, 1>(s, a); break;
+        case 0: e = launch_t2_variant<T, 16, 1>(s, a, CFG_T2 + 0); break;
+        case 1: e = launch_t2_variant<T, 8, 2>(s, a, CFG_T2 + 1); break;
+        case 2: e = launch_t2_variant<T, 12, 1>(s, a, CFG_T2 + 2); break;
 #ifdef FDTD_T2_ABLATE   /* timing experiments only: results are wrong */
-        case 11: e = launch_t2_variant<T, 16, 1, 1>(s, a); break;
-        case 12: e = launch_t2_variant<T, 16, 1, 2>(s, a); break;
-        case 13: e = launch_t2_variant<T, 16, 1, 3>(s, a); break;
-        case 14: e = launch_t2_variant<T, 16, 1, 4>(s, a); break;
+        case 11: e = launch_t2_variant<T, 16, 1, 1>(s, a, CFG_T2 + 3); break;
+        case 12: e = launch_t2_variant<T, 16, 1, 2>(s, a, CFG_T2 + 4); break;
+        case 13: e = launch_t2_variant<T, 16, 1, 3>(s, a, CFG_T2 + 5); break;
+        case 14: e = launch_t2_variant<T, 16, 1, 4>(s, a, CFG_T2 + 6); break;
 #endif
     }
     if (e != cudaSuccess) return cuda_fail(e, "fused_BE_T2_kernel launch");
@@ -469,15 +465,44 @@ static char* plane_ptr(const Solver* s, int comp, int gen, int local_plane) {
     return static_cast<char*>(s->p[comp][gen]) + (long long)local_plane * s->g.plane * (long long)s->esz;
 }
 
+// Exchange lists.  One entry = a contiguous range of planes of one array, described both ways: as a send / recv pair for
+// the NCCL transport and as a push into the neighbour's ghost planes for the copy-engine transport (peer_ring.cu).
+struct XferList {
+    PlaneXfer x[24];
+    int n = 0;
+};
+// my planes [src, src + np) -> the upper neighbour's bottom ghost planes [dst, dst + np), dst < 0 (the mirror image arrives
+// from the lower neighbour into my own planes [dst, dst + np))
+static void push_up(const Solver* s, XferList& l, int comp, int gen, int src, int dst, int np) {
+    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
+    const size_t bytes = (size_t)s->g.plane * s->esz * np;
+    l.x[l.n++] = PlaneXfer{plane_ptr(s, comp, gen, src), up, plane_ptr(s, comp, gen, dst), down, bytes, 1, comp, gen, dst};
+}
+// my planes [src, src + np) -> the lower neighbour's top ghost planes nk_peer + [d, d + np) (mirror: from the upper
+// neighbour into my planes nk + [d, d + np))
+static void push_down(const Solver* s, XferList& l, int comp, int gen, int src, int d, int np) {
+    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
+    const size_t bytes = (size_t)s->g.plane * s->esz * np;
+    l.x[l.n++] = PlaneXfer{plane_ptr(s, comp, gen, src), down, plane_ptr(s, comp, gen, s->g.nk + d), up, bytes, 0, comp, gen, d};
+}
+
+// Both transports have the same meaning on `stream`: when the call's work has run, the ghost planes hold the neighbours'
+// planes -- except wait_data = false on the peer transport, where the consumer (the T2 pass kernel) waits itself.
+static fdtd_status_t ring_exchange(Solver* s, const XferList& l, cudaStream_t stream, bool wait_data = true,
+                                   cudaEvent_t ev_start = nullptr, cudaEvent_t ev_end = nullptr) {
+    if (s->peer) return peer_exchange(s, l.x, l.n, stream, wait_data, ev_start, ev_end);
+    if (ev_start) FDTD_CUDA_TRY(cudaEventRecord(ev_start, stream));
+    fdtd_status_t st = nccl_exchange(s, l.x, l.n, stream);
+    if (st == FDTD_OK && ev_end) FDTD_CUDA_TRY(cudaEventRecord(ev_end, stream));
+    return st;
+}
+
 // Top ghost of Ex,Ey <- upper neighbour's bottom plane (coarray/fdtd.F90:97-98).
 static fdtd_status_t exchange_E_top(Solver* s) {
     if (s->cfg.nranks <= 1 || s->ghosts_e_valid) return FDTD_OK;
-    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
-    const size_t bytes = (size_t)s->g.plane * s->esz;
-    PlaneXfer x[2];
-    for (int c = 0; c < 2; ++c)
-        x[c] = PlaneXfer{plane_ptr(s, EX + c, s->cur, 0), down, plane_ptr(s, EX + c, s->cur, s->g.nk), up, bytes};
-    fdtd_status_t st = nccl_exchange(s, x, 2, s->stream);
+    XferList l;
+    for (int c = 0; c < 2; ++c) push_down(s, l, EX + c, s->cur, 0, 0, 1);
+    fdtd_status_t st = ring_exchange(s, l, s->stream);
     if (st == FDTD_OK) s->ghosts_e_valid = true;
     return st;
 }
@@ -485,12 +510,9 @@ static fdtd_status_t exchange_E_top(Solver* s) {
 // Bottom ghost of Bx,By <- lower neighbour's top plane (coarray/fdtd.F90:90-91).
 static fdtd_status_t exchange_B_bottom(Solver* s) {
     if (s->cfg.nranks <= 1 || s->ghosts_b_valid) return FDTD_OK;
-    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
-    const size_t bytes = (size_t)s->g.plane * s->esz;
-    PlaneXfer x[2];
-    for (int c = 0; c < 2; ++c)
-        x[c] = PlaneXfer{plane_ptr(s, BX + c, s->cur, s->g.nk - 1), up, plane_ptr(s, BX + c, s->cur, -1), down, bytes};
-    fdtd_status_t st = nccl_exchange(s, x, 2, s->stream);
+    XferList l;
+    for (int c = 0; c < 2; ++c) push_up(s, l, BX + c, s->cur, s->g.nk - 1, -1, 1);
+    fdtd_status_t st = ring_exchange(s, l, s->stream);
     if (st == FDTD_OK) s->ghosts_b_valid = true;
     return st;
 }
@@ -498,43 +520,31 @@ static fdtd_status_t exchange_B_bottom(Solver* s) {
 // Everything the fused pass needs: bottom ghost of Bx,By,Ex,Ey,Ez (to rebuild B'(-1)) and top ghost of Ex,Ey.
 static fdtd_status_t exchange_fused(Solver* s, cudaStream_t stream) {
     if (s->cfg.nranks <= 1 || s->ghosts_fused_valid) return FDTD_OK;
-    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
-    const size_t bytes = (size_t)s->g.plane * s->esz;
-    PlaneXfer x[7];
+    XferList l;
     const int up_comps[5] = {BX, BY, EX, EY, EZ};
-    int n = 0;
-    for (int c = 0; c < 5; ++c)
-        x[n++] = PlaneXfer{plane_ptr(s, up_comps[c], s->cur, s->g.nk - 1), up, plane_ptr(s, up_comps[c], s->cur, -1), down, bytes};
-    for (int c = 0; c < 2; ++c)
-        x[n++] = PlaneXfer{plane_ptr(s, EX + c, s->cur, 0), down, plane_ptr(s, EX + c, s->cur, s->g.nk), up, bytes};
-    fdtd_status_t st = nccl_exchange(s, x, n, stream);
+    for (int c = 0; c < 5; ++c) push_up(s, l, up_comps[c], s->cur, s->g.nk - 1, -1, 1);
+    for (int c = 0; c < 2; ++c) push_down(s, l, EX + c, s->cur, 0, 0, 1);
+    fdtd_status_t st = ring_exchange(s, l, stream);
     if (st == FDTD_OK) { s->ghosts_fused_valid = true; s->ghosts_e_valid = true; s->ghosts_b_valid = true; }
     return st;
 }
 
 // Everything the T2 pass needs: two bottom ghost planes of E, B (to rebuild B1(-2), B1(-1), E1(-1)) plus J(-1),
 // top ghost plane nk of E, B, J (B1(nk), E1(nk)) and top ghost plane nk+1 of Ex, Ey.  J travels because stage A
-// re-computes the neighbour's boundary plane, current term included.
-static fdtd_status_t exchange_t2(Solver* s, cudaStream_t stream) {
+// re-computes the neighbour's boundary plane, current term included.  26 planes each way, 18 contiguous ranges.
+static fdtd_status_t exchange_t2(Solver* s, cudaStream_t stream, bool wait_data = true, cudaEvent_t ev_start = nullptr,
+                                 cudaEvent_t ev_end = nullptr) {
     if (s->cfg.nranks <= 1 || s->ghosts_t2_valid) return FDTD_OK;
-    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
-    const size_t bytes = (size_t)s->g.plane * s->esz;
     const int nk = s->g.nk;
-    PlaneXfer x[32];
-    int n = 0;
-    auto gen = [&](int c) { return c < JX ? s->cur : 0; };
+    XferList l;
     // to the upper neighbour: our top planes nk-2, nk-1 become its planes -2, -1
-    for (int c = EX; c <= BZ; ++c)
-        for (int d = 1; d <= 2; ++d)
-            x[n++] = PlaneXfer{plane_ptr(s, c, gen(c), nk - d), up, plane_ptr(s, c, gen(c), -d), down, bytes};
-    for (int c = JX; c <= JZ; ++c)
-        x[n++] = PlaneXfer{plane_ptr(s, c, 0, nk - 1), up, plane_ptr(s, c, 0, -1), down, bytes};
+    for (int c = EX; c <= BZ; ++c) push_up(s, l, c, s->cur, nk - 2, -2, 2);
+    for (int c = JX; c <= JZ; ++c) push_up(s, l, c, 0, nk - 1, -1, 1);
     // to the lower neighbour: our bottom plane 0 becomes its plane nk (E, B, J), our plane 1 its plane nk+1 (Ex, Ey)
-    for (int c = EX; c <= JZ; ++c)
-        x[n++] = PlaneXfer{plane_ptr(s, c, gen(c), 0), down, plane_ptr(s, c, gen(c), nk), up, bytes};
-    for (int c = EX; c <= EY; ++c)
-        x[n++] = PlaneXfer{plane_ptr(s, c, s->cur, 1), down, plane_ptr(s, c, s->cur, nk + 1), up, bytes};
-    fdtd_status_t st = nccl_exchange(s, x, n, stream);
+    for (int c = EX; c <= EY; ++c) push_down(s, l, c, s->cur, 0, 0, 2);
+    for (int c = EZ; c <= BZ; ++c) push_down(s, l, c, s->cur, 0, 0, 1);
+    for (int c = JX; c <= JZ; ++c) push_down(s, l, c, 0, 0, 0, 1);
+    fdtd_status_t st = ring_exchange(s, l, stream, wait_data, ev_start, ev_end);
     if (st == FDTD_OK) { s->ghosts_t2_valid = true; s->ghosts_fused_valid = true; s->ghosts_e_valid = true; s->ghosts_b_valid = true; }
     return st;
 }
@@ -544,14 +554,12 @@ static fdtd_status_t exchange_t2(Solver* s, cudaStream_t stream) {
 // are meaningful on both sides, and only those are read).
 static fdtd_status_t exchange_pair_planes(Solver* s, bool b_to_upper, int gen) {
     if (s->cfg.nranks <= 1) return FDTD_OK;
-    const int up = (s->cfg.rank + 1) % s->cfg.nranks, down = (s->cfg.rank + s->cfg.nranks - 1) % s->cfg.nranks;
-    const size_t bytes = (size_t)s->g.plane * s->esz;
-    PlaneXfer x[2];
+    XferList l;
     for (int c = 0; c < 2; ++c) {
-        if (b_to_upper) x[c] = PlaneXfer{plane_ptr(s, BX + c, gen, s->g.nk - 1), up, plane_ptr(s, BX + c, gen, -1), down, bytes};
-        else x[c] = PlaneXfer{plane_ptr(s, EX + c, gen, 0), down, plane_ptr(s, EX + c, gen, s->g.nk), up, bytes};
+        if (b_to_upper) push_up(s, l, BX + c, gen, s->g.nk - 1, -1, 1);
+        else push_down(s, l, EX + c, gen, 0, 0, 1);
     }
-    return nccl_exchange(s, x, 2, s->stream);
+    return ring_exchange(s, l, s->stream);
 }
 
 static void invalidate_ghosts(Solver* s) {
@@ -623,62 +631,83 @@ static fdtd_status_t materialize_J(Solver* s) {
     return DISPATCH(s, launch_source, s, s->src_amp[s->src_t - 1], 0);
 }
 
-static bool t2_disabled_by_env() {
-    const char* e = std::getenv("FDTD_B200_NO_T2");
-    return e && std::atoi(e) != 0;
+// ---- per-pass timeline (fdtd_timeline_enable): four timing events per overlapped pass -------------------------------
+//   [0] pass start (compute stream, before anything of the pass)      [1] halo copies start (after the ready handshake)
+//   [2] halo copies issued and done on this rank's side               [3] pass end (compute stream, kernels + halo)
+static cudaEvent_t tl_event(Solver* s, int which) {
+    if (s->tl_n >= s->tl_cap) return nullptr;
+    return s->tl_events[(size_t)s->tl_n * 4 + which];
 }
 
-// One launch group over the slab with the halo exchange overlapped: interior planes [H, nk-H) never touch a ghost
-// plane and run while the ring exchange is in flight on the comm stream; the two boundary slabs follow (as one
-// launch when the kernel takes two plane ranges).  launch(lo, hi, lo2, hi2): second range empty when lo2 == hi2.
+// One launch group over the slab with the halo exchange overlapped.  launch(lo, hi, lo2, hi2, halo_seq): second plane
+// range empty when lo2 == hi2; halo_seq != 0 = the kernel waits for exchange number halo_seq itself.
 //
-// Three streams.  The pass kernels own every SM (one 512-thread CTA holds the whole register file), so (1) the comm
-// stream has the highest priority: NCCL's few CTAs are dispatched to the first SMs that free up instead of behind
-// the interior launch's ~1500 pending CTAs, and the planes land early in the pass; (2) the boundary slabs go to a
-// third, normal-priority stream: they read only the input generation and write planes the interior launch does not,
-// so they are independent of it, and their short CTAs are dispatched when the interior launch has no CTA left to
-// issue -- they fill its partial last wave instead of adding launches after it.
+// (A) peer transport + T2 pass (the default on a ring): ONE launch over the whole slab.  The copy engines push the 26
+//     boundary planes into the neighbours' ghost planes while the pass runs; the chunks that read ghost planes are issued
+//     last (chunk order 1 .. nz-1, 0) and their CTAs wait on the sequence flags -- no boundary launch, no redundant plane
+//     iterations, no SM ever runs anything but the pass:
+//        comm stream    : wait(previous work) -> ready handshake -> plane copies -> data flags -> ev_b
+//        compute stream : the pass (whole slab) -> wait(ev_b: our planes have left before the next pass overwrites them)
+// (B) NCCL transport, or a kernel that cannot wait: three streams.  The pass kernels own every SM (one 512-thread CTA holds
+//     the whole register file), so (1) the comm stream has the highest priority: NCCL's few CTAs are dispatched to the first
+//     SMs that free up instead of behind the interior launch's ~1500 pending CTAs; (2) the boundary slabs go to a third,
+//     normal-priority stream: they read only the input generation and write planes the interior launch does not, so they are
+//     independent of it, and their short CTAs fill its partial last wave:
+//        comm stream    : wait(previous work) -> ring exchange into the ghost planes -> ev_b
+//        compute stream : interior planes [H, nk-H) ........................................ -> wait(ev_c)
+//        boundary stream: wait(previous work, ev_b) -> the two boundary slabs -> ev_c
 // FDTD_B200_MGPU_DEBUG (timing experiments only, tools/mgpu_probe.py): bit 0 = no overlap, bit 1 = skip the exchange
 // (wrong fields), bit 2 = boundary slabs on the compute stream (after the interior launch), bit 3 = comm stream without
-// priority (read when the solver is created), bits 8.. = boundary depth H.
-static int mgpu_debug() {
-    const char* e = std::getenv("FDTD_B200_MGPU_DEBUG");
-    return e ? std::atoi(e) : 0;
-}
-
+// priority, bit 4 = structure (B) on the peer transport, bits 8.. = boundary depth H.
 template <typename LaunchFn, typename ExchangeFn>
-static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, LaunchFn launch, ExchangeFn exchange_in) {
-    const int dbg = (s->cfg.nranks > 1) ? mgpu_debug() : 0;
+static fdtd_status_t overlapped(Solver* s, bool ghosts_valid, bool kernel_can_wait, LaunchFn launch, ExchangeFn exchange_in) {
+    const int dbg = (s->cfg.nranks > 1) ? s->tun.mgpu_debug : 0;
     const int H = (dbg >> 8) > 0 ? (dbg >> 8) : 2;   // boundary depth (planes) computed after the halo has landed (>= 2: the T2 pass reads k +- 2)
-    auto exchange = [&](cudaStream_t q) -> fdtd_status_t { return (dbg & 2) ? FDTD_OK : exchange_in(q); };
+    auto exchange = [&](cudaStream_t q, bool wait, cudaEvent_t e0, cudaEvent_t e1) -> fdtd_status_t {
+        return (dbg & 2) ? FDTD_OK : exchange_in(q, wait, e0, e1);
+    };
     fdtd_status_t st;
     s->launch_stream = s->stream;
-    if (s->cfg.nranks > 1 && !ghosts_valid && H >= 2 && s->g.nk >= 4 * H && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP) && !(dbg & 1)) {
-        // north_star (d): halo exchange on its own stream, overlapped with the interior chunks.
-        //   comm stream    : wait(previous work) -> ring exchange into the ghost planes -> ev_b
-        //   compute stream : interior planes [H, nk-H) ........................................ -> wait(ev_c)
-        //   boundary stream: wait(previous work, ev_b) -> the two boundary slabs -> ev_c
+    const bool ring = s->cfg.nranks > 1 && !ghosts_valid && !(s->cfg.flags & FDTD_FLAG_NO_OVERLAP) && !(dbg & 1);
+    const bool timeline = ring && s->tl_n < s->tl_cap;
+    if (timeline) FDTD_CUDA_TRY(cudaEventRecord(tl_event(s, 0), s->stream));
+    if (ring && s->peer && s->halo_in_kernel && kernel_can_wait && !(dbg & (2 | 16))) {
         FDTD_CUDA_TRY(cudaEventRecord(s->ev_a, s->stream));
         FDTD_CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
-        if ((st = exchange(s->comm_stream)) != FDTD_OK) return st;
+        if ((st = exchange(s->comm_stream, false, timeline ? tl_event(s, 1) : nullptr, timeline ? tl_event(s, 2) : nullptr)) != FDTD_OK) return st;
         FDTD_CUDA_TRY(cudaEventRecord(s->ev_b, s->comm_stream));
-        if ((st = launch(H, s->g.nk - H, 0, 0)) != FDTD_OK) return st;
-        if (dbg & 4) {
-            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
-            return launch(0, H, s->g.nk - H, s->g.nk);
-        }
-        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->bnd_stream, s->ev_a, 0));
-        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->bnd_stream, s->ev_b, 0));
-        s->launch_stream = s->bnd_stream;
-        st = launch(0, H, s->g.nk - H, s->g.nk);
-        s->launch_stream = s->stream;
-        if (st != FDTD_OK) return st;
-        FDTD_CUDA_TRY(cudaEventRecord(s->ev_c, s->bnd_stream));
-        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_c, 0));
+        if ((st = launch(0, s->g.nk, 0, 0, peer_last_seq(s))) != FDTD_OK) return st;
+        // whatever follows on the compute stream may read any ghost plane (PML rim sweeps; a rank whose T2 launch was
+        // clipped away from a slab boundary never waited in the kernel): satisfied long ago, costs two front-end ops
+        if ((st = peer_wait_data(s, s->stream)) != FDTD_OK) return st;
+        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
+        if (timeline) { FDTD_CUDA_TRY(cudaEventRecord(tl_event(s, 3), s->stream)); s->tl_n++; }
         return FDTD_OK;
     }
-    if ((st = exchange(s->stream)) != FDTD_OK) return st;
-    return launch(0, s->g.nk, 0, 0);
+    if (ring && H >= 2 && s->g.nk >= 4 * H) {
+        FDTD_CUDA_TRY(cudaEventRecord(s->ev_a, s->stream));
+        FDTD_CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
+        if ((st = exchange(s->comm_stream, true, timeline ? tl_event(s, 1) : nullptr, timeline ? tl_event(s, 2) : nullptr)) != FDTD_OK) return st;
+        FDTD_CUDA_TRY(cudaEventRecord(s->ev_b, s->comm_stream));
+        if ((st = launch(H, s->g.nk - H, 0, 0, 0u)) != FDTD_OK) return st;
+        if (dbg & 4) {
+            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_b, 0));
+            st = launch(0, H, s->g.nk - H, s->g.nk, 0u);
+        } else {
+            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->bnd_stream, s->ev_a, 0));
+            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->bnd_stream, s->ev_b, 0));
+            s->launch_stream = s->bnd_stream;
+            st = launch(0, H, s->g.nk - H, s->g.nk, 0u);
+            s->launch_stream = s->stream;
+            if (st != FDTD_OK) return st;
+            FDTD_CUDA_TRY(cudaEventRecord(s->ev_c, s->bnd_stream));
+            FDTD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_c, 0));
+        }
+        if (st == FDTD_OK && timeline) { FDTD_CUDA_TRY(cudaEventRecord(tl_event(s, 3), s->stream)); s->tl_n++; }
+        return st;
+    }
+    if ((st = exchange(s->stream, true, nullptr, nullptr)) != FDTD_OK) return st;
+    return launch(0, s->g.nk, 0, 0, 0u);
 }
 
 // PML solver, two steps in one pass.  Reach of the T2 pass is 2 cells, so it is exact on the store box
@@ -705,17 +734,18 @@ static fdtd_status_t advance_pml_pair(Solver* s, int n_half, int src2, double am
     fdtd_status_t st;
     // local planes of the store box on this rank (possibly none: a rank inside the k shell only runs rim sweeps)
     const int klo = std::max(s->sb_lo[2] - s->g.k0, 0), khi = std::min(s->sb_hi[2] - s->g.k0, s->g.nk);
-    auto t2_clipped = [&](int lo, int hi, int lo2, int hi2) -> fdtd_status_t {
+    auto t2_clipped = [&](int lo, int hi, int lo2, int hi2, unsigned halo_seq) -> fdtd_status_t {
         lo = std::max(lo, klo); hi = std::min(hi, khi);
         lo2 = std::max(lo2, klo); hi2 = std::min(hi2, khi);
         if (hi <= lo) { lo = lo2; hi = hi2; lo2 = hi2 = 0; }
         if (hi2 <= lo2) lo2 = hi2 = 0;
         if (hi <= lo) return FDTD_OK;
-        return DISPATCH(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2);
+        return DISPATCH(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2, halo_seq);
     };
     // slab ranks: ring exchange of the two ghost planes per side (+ J) overlapped with the interior planes, as in the
     // periodic solver; single GPU: one launch
-    st = overlapped(s, s->ghosts_t2_valid, t2_clipped, [&](cudaStream_t q) { return exchange_t2(s, q); });
+    st = overlapped(s, s->ghosts_t2_valid, true, t2_clipped,
+                    [&](cudaStream_t q, bool wait, cudaEvent_t e0, cudaEvent_t e1) { return exchange_t2(s, q, wait, e0, e1); });
     if (st != FDTD_OK) return st;
     int lo[3], hi[3];
     shrink_box(s, 2, 2 * V, lo, hi);
@@ -755,7 +785,7 @@ static fdtd_status_t advance(Solver* s, int remaining, int* done) {
         }
     }
     const int n_half = s->b_pending ? 2 : 1;
-    if (s->pml_t2 && remaining >= 2 && !t2_disabled_by_env() &&
+    if (s->pml_t2 && remaining >= 2 && !s->tun.no_t2 &&
         !(s->src_active && s->src_t >= (int)s->src_amp.size())) {   // (the source does not retire between the two steps)
         const int src2 = s->src_active ? 1 : 0;
         const double amp2 = src2 ? s->src_amp[s->src_t] : 0.0;
@@ -768,24 +798,24 @@ static fdtd_status_t advance(Solver* s, int remaining, int* done) {
     } else if (s->fused) {
         // Pair this step with the next one unless the source retires in between (J would have to change to zero).
         const bool src_ends = s->src_active && s->src_t >= (int)s->src_amp.size();
-        if (s->t2 && remaining >= 2 && !src_ends && !t2_disabled_by_env()) {
+        if (s->t2 && remaining >= 2 && !src_ends && !s->tun.no_t2) {
             const int src2 = s->src_active ? 1 : 0;
             const double amp2 = src2 ? s->src_amp[s->src_t] : 0.0;
-            st = overlapped(s, s->ghosts_t2_valid,
-                            [&](int lo, int hi, int lo2, int hi2) { return DISPATCH(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2); },
-                            [&](cudaStream_t q) { return exchange_t2(s, q); });
+            st = overlapped(s, s->ghosts_t2_valid, true,
+                            [&](int lo, int hi, int lo2, int hi2, unsigned halo_seq) { return DISPATCH(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2, halo_seq); },
+                            [&](cudaStream_t q, bool wait, cudaEvent_t e0, cudaEvent_t e1) { return exchange_t2(s, q, wait, e0, e1); });
             if (st != FDTD_OK) return st;
             if (src2) { s->src_t++; s->j_stale = true; }
             s->passes_t2++;
             *done = 2;
         } else {
-            st = overlapped(s, s->ghosts_fused_valid,
-                            [&](int lo, int hi, int lo2, int hi2) {
+            st = overlapped(s, s->ghosts_fused_valid, false,
+                            [&](int lo, int hi, int lo2, int hi2, unsigned) {
                                 fdtd_status_t r = DISPATCH(s, launch_fused, s, n_half, lo, hi);
                                 if (r == FDTD_OK && hi2 > lo2) r = DISPATCH(s, launch_fused, s, n_half, lo2, hi2);
                                 return r;
                             },
-                            [&](cudaStream_t q) { return exchange_fused(s, q); });
+                            [&](cudaStream_t q, bool, cudaEvent_t, cudaEvent_t) { return exchange_fused(s, q); });
             if (st != FDTD_OK) return st;
         }
         s->cur ^= 1;
@@ -831,6 +861,7 @@ static void destroy_impl(Solver* s) {
     if (s->ev_a) cudaEventDestroy(s->ev_a);
     if (s->ev_b) cudaEventDestroy(s->ev_b);
     if (s->ev_c) cudaEventDestroy(s->ev_c);
+    for (cudaEvent_t e : s->tl_events) cudaEventDestroy(e);
     if (s->bnd_stream) cudaStreamDestroy(s->bnd_stream);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -872,6 +903,8 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
     Solver* s = new (std::nothrow) Solver();
     if (!s) return fail(FDTD_ERR_NOMEM, "out of host memory");
     s->cfg = *cfg;
+    read_tunables(s->tun);
+    { const char* e = std::getenv("FDTD_B200_HALO_IN_KERNEL"); s->halo_in_kernel = !(e && std::atoi(e) == 0); }
     s->device = dev;
     s->dtype = cfg->dtype;
     s->esz = (cfg->dtype == FDTD_F32) ? 4 : 8;
@@ -914,24 +947,26 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
     {
         int prio_lo = 0, prio_hi = 0;   // numerically lower = higher priority
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        { const char* e = std::getenv("FDTD_B200_MGPU_DEBUG"); if (e && (std::atoi(e) & 8)) prio_hi = prio_lo; }   // bit 3 (read here): no priority
+        if (s->tun.mgpu_debug & 8) prio_hi = prio_lo;   // bit 3: no priority
         if (cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
     }
     if (cudaStreamCreateWithFlags(&s->bnd_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
     s->launch_stream = s->stream;
-    cudaEventCreate(&s->ev_t0); cudaEventCreate(&s->ev_t1);
-    cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s->ev_c, cudaEventDisableTiming);
+    if (cudaEventCreate(&s->ev_t0) != cudaSuccess || cudaEventCreate(&s->ev_t1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_c, cudaEventDisableTiming) != cudaSuccess)
+        return bail(cuda_fail(cudaGetLastError(), "cudaEventCreate"));
 
     // The fused pass serves the periodic solver with vector-aligned rows; everything else runs the two sweeps.
     const int V = (int)(16 / s->esz);
     s->fused = !s->has_pml && !(cfg->flags & FDTD_FLAG_NO_FUSION) && (P.Ni % V == 0);
-    s->t2 = s->fused && !(cfg->flags & FDTD_FLAG_NO_TEMPORAL) && s->g.nk >= 4;
+    // (decided from the smallest slab of the ring, not the local one: every rank must take the same path, or the
+    // exchange plans of neighbours do not match -- fdtd_slab_range gives the remainder planes to the low ranks)
+    s->t2 = s->fused && !(cfg->flags & FDTD_FLAG_NO_TEMPORAL) && P.Nk / cfg->nranks >= 4;
     // fp64 by default: the fp32 T2 pass is conversion-bound and loses to the two lean interior sweeps
     // (measured 5.5 vs 4.8 ms per step at 512^3); FDTD_B200_PML_T2_F32=1 turns it on anyway (parity tests do).
-    const char* f32_pair = std::getenv("FDTD_B200_PML_T2_F32");
-    const bool pair_dtype_ok = (s->esz == 8) || (f32_pair && std::atoi(f32_pair) != 0);
+    const bool pair_dtype_ok = (s->esz == 8) || s->tun.pml_t2_f32;
     if (s->has_pml && pair_dtype_ok && !(cfg->flags & (FDTD_FLAG_NO_FUSION | FDTD_FLAG_NO_TEMPORAL)) && (P.Ni % V == 0) && P.Nk / cfg->nranks >= 4) {
         // store box of the two-step pass: main box shrunk by the pass's reach on the axes that have a shell
         bool ok = true;
@@ -961,8 +996,12 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
             if (cudaMalloc(&s->d_decay[a], sizeof(double) * N[a]) != cudaSuccess ||
                 cudaMalloc(&s->d_coef2[a], sizeof(double) * N[a]) != cudaSuccess)
                 return bail(cuda_fail(cudaGetLastError(), "cudaMalloc(pml tables)"));
-            cudaMemcpy(s->d_decay[a], dec.data(), sizeof(double) * N[a], cudaMemcpyHostToDevice);
-            cudaMemcpy(s->d_coef2[a], c2.data(), sizeof(double) * N[a], cudaMemcpyHostToDevice);
+            // on the solver's own (non-blocking) stream: the kernels that read the tables are ordered after the copies
+            // (pageable source: the call returns once the data is staged, the vectors may die at the end of this scope)
+            if (cudaMemcpyAsync(s->d_decay[a], dec.data(), sizeof(double) * N[a], cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+                cudaMemcpyAsync(s->d_coef2[a], c2.data(), sizeof(double) * N[a], cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+                cudaStreamSynchronize(s->stream) != cudaSuccess)
+                return bail(cuda_fail(cudaGetLastError(), "cudaMemcpy(pml tables)"));
         }
     }
     jbox_clear(s);
@@ -1003,11 +1042,6 @@ static fdtd_status_t enter(fdtd_solver_t* h, Solver** s) {
     fdtd_status_t st = check_handle(h, s);
     if (st != FDTD_OK) return st;
     return flush_lazy(*s);
-}
-
-static bool lazy_disabled_by_env() {
-    const char* e = std::getenv("FDTD_B200_NO_LAZY");
-    return e && std::atoi(e) != 0;
 }
 
 static fdtd_status_t check_component(int comp) {
@@ -1185,7 +1219,7 @@ fdtd_status_t fdtd_update_fields(fdtd_solver_t* h) {
         s->lazy_steps = 0;
         return run_steps(s, 2);
     }
-    if ((s->t2 || s->pml_t2) && !t2_disabled_by_env() && !lazy_disabled_by_env()) {
+    if ((s->t2 || s->pml_t2) && !s->tun.no_t2 && !s->tun.no_lazy) {
         s->lazy_steps = 1;
         return FDTD_OK;
     }
@@ -1286,6 +1320,10 @@ fdtd_status_t fdtd_read_slice(fdtd_solver_t* h, int comp, int axis, int index, v
     if (count_out) *count_out = 0;
     const int N[3] = {s->g.Ni, s->g.Nj, s->g.Nk};
     if (axis < 0 || axis > 2 || index < 0 || index >= N[axis]) return fail(FDTD_ERR_BAD_ARGUMENT, "read_slice: axis / index out of range");
+    // Collective part first (every rank of a multi-rank solver must get here, whoever owns the plane): the deferred B
+    // half step needs the Ex, Ey ring exchange.  Only then the ownership test.
+    if (comp >= BX && comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
+    if (comp >= JX && (st = materialize_J(s)) != FDTD_OK) return st;
     int n0, n1, local = index;
     if (axis == 2) {
         n0 = s->g.Ni; n1 = s->g.Nj; local = index - s->g.k0;
@@ -1295,8 +1333,6 @@ fdtd_status_t fdtd_read_slice(fdtd_solver_t* h, int comp, int axis, int index, v
     }
     const size_t n = (size_t)n0 * n1;
     if (!host || capacity < n) return fail(FDTD_ERR_BAD_ARGUMENT, "read_slice: host buffer too small");
-    if (comp >= BX && comp < JX && (st = flush_pending(s)) != FDTD_OK) return st;
-    if (comp >= JX && (st = materialize_J(s)) != FDTD_OK) return st;
     st = (s->dtype == FDTD_F32) ? slice_impl<float>(s, comp, axis, local, n0, n1, host) : slice_impl<double>(s, comp, axis, local, n0, n1, host);
     if (st == FDTD_OK && count_out) *count_out = n;
     return st;
@@ -1318,10 +1354,11 @@ fdtd_status_t fdtd_set_source(fdtd_solver_t* h, const int lo[3], const int hi[3]
         const int n = hi[a] - lo[a];
         if (n > 0) {
             FDTD_CUDA_TRY(cudaMalloc(&s->d_w[a], sizeof(double) * n));
-            FDTD_CUDA_TRY(cudaMemcpy(s->d_w[a], w[a], sizeof(double) * n, cudaMemcpyHostToDevice));
+            FDTD_CUDA_TRY(cudaMemcpyAsync(s->d_w[a], w[a], sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
         }
         s->src_lo[a] = lo[a]; s->src_hi[a] = hi[a];
     }
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));   // the caller's tables may be freed after this call
     s->src_amp.assign(amp, amp + n_amp);
     s->src_t = 0;
     s->src_active = true;
@@ -1342,6 +1379,11 @@ fdtd_status_t fdtd_sync(fdtd_solver_t* h) {
     if (st != FDTD_OK) return st;
     if ((st = flush_pending(s)) != FDTD_OK) return st;
     FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (unsigned* err = peer_error_word(s)) {
+        unsigned v = 0;
+        FDTD_CUDA_TRY(cudaMemcpy(&v, err, sizeof(v), cudaMemcpyDeviceToHost));
+        if (v) return fail(FDTD_ERR_STATE, "halo wait timed out inside the pass kernel (a neighbour rank never pushed its planes): fields are invalid");
+    }
     return FDTD_OK;
 }
 
@@ -1374,6 +1416,8 @@ fdtd_status_t fdtd_get_info(fdtd_solver_t* h, fdtd_info_t* info) {
     info->rank = s->cfg.rank; info->nranks = s->cfg.nranks; info->device = s->device;
     info->temporal = (s->t2 || s->pml_t2) ? 1 : 0;
     info->passes_t2 = s->passes_t2;
+    info->transport = s->cfg.nranks <= 1 ? 0 : (s->peer ? 2 : (s->comm ? 1 : 0));
+    info->halo_in_kernel = (s->peer && s->halo_in_kernel) ? 1 : 0;
     return FDTD_OK;
 }
 
@@ -1413,6 +1457,48 @@ fdtd_status_t fdtd_comm_init(fdtd_solver_t* h, const void* id, size_t id_bytes) 
     fdtd_status_t st = check_handle(h, &s);
     if (st != FDTD_OK) return st;
     return nccl_init(s, id, id_bytes);
+}
+
+fdtd_status_t fdtd_comm_init_local(fdtd_solver_t** solvers, int n) {
+    if (!solvers || n < 1) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    for (int i = 0; i < n; ++i) if (!solvers[i]) return fail(FDTD_ERR_BAD_ARGUMENT, "null solver handle");
+    return peer_ring_init_local(reinterpret_cast<Solver**>(solvers), n);
+}
+
+fdtd_status_t fdtd_timeline_enable(fdtd_solver_t* h, int max_passes) {
+    Solver* s;
+    fdtd_status_t st = enter(h, &s);
+    if (st != FDTD_OK) return st;
+    if (max_passes < 0) return fail(FDTD_ERR_BAD_ARGUMENT, "negative pass count");
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (cudaEvent_t e : s->tl_events) cudaEventDestroy(e);
+    s->tl_events.clear();
+    s->tl_cap = s->tl_n = 0;
+    for (int i = 0; i < 4 * max_passes; ++i) {
+        cudaEvent_t e;
+        FDTD_CUDA_TRY(cudaEventCreate(&e));
+        s->tl_events.push_back(e);
+    }
+    s->tl_cap = max_passes;
+    return FDTD_OK;
+}
+
+fdtd_status_t fdtd_timeline_read(fdtd_solver_t* h, double* ms, int capacity_passes, int* n_passes) {
+    Solver* s;
+    fdtd_status_t st = enter(h, &s);
+    if (st != FDTD_OK) return st;
+    if (!n_passes || (capacity_passes > 0 && !ms)) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->comm_stream));
+    const int n = s->tl_n < capacity_passes ? s->tl_n : capacity_passes;
+    for (int p = 0; p < n; ++p)
+        for (int w = 0; w < 4; ++w) {
+            float t = 0.f;
+            FDTD_CUDA_TRY(cudaEventElapsedTime(&t, s->tl_events[0], s->tl_events[(size_t)p * 4 + w]));
+            ms[p * 4 + w] = (double)t;
+        }
+    *n_passes = n;
+    return FDTD_OK;
 }
 
 }  // extern "C"

@@ -88,6 +88,14 @@ struct FusedT2Args {
     // output tile misses it exit at once.  The whole grid for the periodic solver; the main box shrunk by the pass's
     // dependency reach (2 cells) for the PML solver, whose shell and rim are advanced by the sweep kernels.
     int sb_lo[2], sb_hi[2];
+    // Halo hand-off inside the kernel (z-slab rank on the peer transport, csrc/peer_ring.cu): the neighbours' copy engines
+    // push their boundary planes into this rank's ghost planes while the pass runs and then set halo_flags[0] (lower
+    // neighbour) / halo_flags[1] (upper neighbour) to the exchange number.  A CTA whose chunk reads ghost planes waits
+    // until the flag has reached halo_seq; z_rot issues those chunks last (chunk order 1, 2, ..., nz-1, 0).
+    const unsigned* halo_flags;   // nullptr: nothing to wait for
+    unsigned* halo_err;           // set to 1 when a wait gives up (2 s): the host reports it at fdtd_sync
+    unsigned halo_seq;
+    int z_rot;
     alignas(64) CUtensorMap tmE[3];
     alignas(64) CUtensorMap tmB[3];
 };
@@ -248,6 +256,30 @@ __device__ __forceinline__ void t2_update_E(double (&e)[3][T2_V], const double (
         e[0][q] = t2_round<T>(dadd(e[0][q], dsub(tx_, dmul(cEz, dsub(by, byk[q])))));
         e[1][q] = t2_round<T>(dadd(e[1][q], dsub(ty_, dmul(cEx, dsub(bz, bzl)))));
         e[2][q] = t2_round<T>(dadd(e[2][q], dsub(tz_, dmul(cEy, dsub(bx, bxd[q])))));
+    }
+}
+
+// Plane chunk [kb, ke) of this CTA: blockIdx.z walks the chunks of the first plane range, then those of the second.
+template <typename T>
+__device__ __forceinline__ void t2_chunk_of(const FusedT2Args<T>& a, int& kb, int& ke) {
+    int z = (int)blockIdx.z;
+    const bool second = z >= a.nz1;
+    if (a.z_rot && !second) { z += 1; if (z == a.nz1) z = 0; }
+    kb = (second ? a.k_lo2 : a.k_lo) + (z - (second ? a.nz1 : 0)) * a.kc;
+    ke = min(kb + a.kc, second ? a.k_hi2 : a.k_hi);
+}
+
+// Wait (one thread, then the CTA) until the neighbour's planes of exchange `seq` have landed in this rank's ghost
+// planes.  The flag is written by the neighbour's copy engine after its plane copies, on the same stream.
+__device__ __forceinline__ void t2_halo_wait(const unsigned* flag, unsigned seq, unsigned* err) {
+    unsigned v;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - seq) >= 0) break;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000LL) { *err = 1u; break; }   // ~2 s: a neighbour died; do not hang the GPU
+        __nanosleep(200);
     }
 }
 
@@ -520,11 +552,7 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     c.out = c.needE2 && lane_active && (tx >= 1) && (tx <= FUSED_OUT_LANES) && (c.i < Ni) &&
             (c.i >= a.sb_lo[0]) && (c.i + V <= a.sb_hi[0]) && (j >= a.sb_lo[1]) && (j < a.sb_hi[1]);
     c.roff = (long long)c.jw * a.g.pitch + (lane_active ? iw : 0);
-    {
-        const bool second = (int)blockIdx.z >= a.nz1;
-        c.kb = (second ? a.k_lo2 : a.k_lo) + ((int)blockIdx.z - (second ? a.nz1 : 0)) * a.kc;
-        c.ke = min(c.kb + a.kc, second ? a.k_hi2 : a.k_hi);
-    }
+    t2_chunk_of(a, c.kb, c.ke);
     // J may be non-zero only inside jbox (global coordinates).  Stage A needs it on every cell whose E1 feeds an
     // output cell, halo lanes / rows included (their wrapped coordinates are tested); stage B only where it stores.
     c.j_ijA = HAS_J && lane_active && row_active && (iw < a.jbox.hi[0]) && (iw + V > a.jbox.lo[0]) &&
@@ -595,9 +623,21 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     const int i0 = tbx * (FUSED_OUT_LANES * V) - V, j0 = tby * (BY - 4) - 2;
     // output tile = [i0 + V, i0 + V + 30 V) x [j0 + 2, j0 + BY - 2)
     if (i0 + V >= a.sb_hi[0] || i0 + V + FUSED_OUT_LANES * V <= a.sb_lo[0] || j0 + 2 >= a.sb_hi[1] || j0 + BY - 2 <= a.sb_lo[1]) return;
-    const bool second = (int)blockIdx.z >= a.nz1;
-    const int kb = (second ? a.k_lo2 : a.k_lo) + ((int)blockIdx.z - (second ? a.nz1 : 0)) * a.kc;
-    const int k0 = a.g.k0 + kb - 2, k1 = a.g.k0 + min(kb + a.kc, second ? a.k_hi2 : a.k_hi) + 1;
+    int kb, ke;
+    t2_chunk_of(a, kb, ke);
+    const int k0 = a.g.k0 + kb - 2, k1 = a.g.k0 + ke + 1;
+    if (a.halo_flags) {
+        // the chunk reads planes kb-2 .. ke+1: ghost planes below 0 come from the lower neighbour, at or above nk from the upper
+        const bool need_dn = kb - 2 < 0, need_up = ke + 1 >= a.g.nk;
+        if (need_dn || need_up) {
+            if (threadIdx.x == 0 && threadIdx.y == 0) {
+                if (need_dn) t2_halo_wait(a.halo_flags + 0, a.halo_seq, a.halo_err);
+                if (need_up) t2_halo_wait(a.halo_flags + 1, a.halo_seq, a.halo_err);
+            }
+            __syncthreads();
+            asm volatile("fence.proxy.async;" ::: "memory");   // the TMA loads of the ghost planes are ordered after the acquire
+        }
+    }
     const bool has_j = !a.jbox.empty() && t2_meets(i0, i0 + FUSED_BX * V, a.jbox.lo[0], a.jbox.hi[0], a.g.Ni) &&
                        t2_meets(j0, j0 + BY, a.jbox.lo[1], a.jbox.hi[1], a.g.Nj) &&
                        t2_meets(k0, k1, a.jbox.lo[2], a.jbox.hi[2], a.g.Nk);

@@ -8,6 +8,7 @@
 // torch process the already-loaded torch-bundled libnccl.so.2 is reused.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -17,7 +18,7 @@ namespace fdtd_b200 {
 
 typedef struct { char internal[FDTD_NCCL_UNIQUE_ID_BYTES]; } nccl_uid_t;
 typedef int nccl_result_t;
-enum { NCCL_CHAR = 0 };   // ncclInt8 / ncclChar
+enum { NCCL_CHAR = 0, NCCL_INT32 = 2, NCCL_MIN = 3 };   // ncclInt8 / ncclChar, ncclInt32, ncclMin
 
 struct NcclApi {
     void* lib = nullptr;
@@ -26,6 +27,7 @@ struct NcclApi {
     nccl_result_t (*CommDestroy)(void*) = nullptr;
     nccl_result_t (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     nccl_result_t (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    nccl_result_t (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     nccl_result_t (*GroupStart)() = nullptr;
     nccl_result_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(nccl_result_t) = nullptr;
@@ -48,6 +50,7 @@ static NcclApi* load_nccl(std::string& err) {
     LOAD(CommDestroy, "ncclCommDestroy")
     LOAD(Send, "ncclSend")
     LOAD(Recv, "ncclRecv")
+    LOAD(AllReduce, "ncclAllReduce")
     LOAD(GroupStart, "ncclGroupStart")
     LOAD(GroupEnd, "ncclGroupEnd")
     LOAD(GetErrorString, "ncclGetErrorString")
@@ -84,10 +87,44 @@ fdtd_status_t nccl_init(Solver* s, const void* id, size_t bytes) {
     nccl_result_t r = api->CommInitRank(&s->comm, s->cfg.nranks, uid, s->cfg.rank);
     if (r != 0) return nccl_fail(api, r, "ncclCommInitRank");
     s->nccl = api;
-    return FDTD_OK;
+    // Default transport: copy engines into peer-mapped ghost planes (peer_ring.cu); the communicator carries the CUDA IPC
+    // handles to the neighbours and stays as the fallback when the ring cannot be mapped (FDTD_B200_TRANSPORT=nccl
+    // forces it -- every rank must use the same setting).
+    const char* tr = std::getenv("FDTD_B200_TRANSPORT");
+    if (tr && std::strcmp(tr, "nccl") == 0) { s->peer_note = "FDTD_B200_TRANSPORT=nccl"; return FDTD_OK; }
+    PeerBootstrap boot;
+    boot.ctx = s;
+    boot.exchange = [](void* ctx, const void* send, int up, int down, void* from_down, int down2, void* from_up, int up2, size_t bytes) -> fdtd_status_t {
+        Solver* s = static_cast<Solver*>(ctx);
+        NcclApi* api = s->nccl;
+        nccl_result_t r = api->GroupStart();
+        if (r == 0) r = api->Send(send, bytes, NCCL_CHAR, up, s->comm, s->stream);
+        if (r == 0) r = api->Send(send, bytes, NCCL_CHAR, down, s->comm, s->stream);
+        if (r == 0) r = api->Recv(from_down, bytes, NCCL_CHAR, down2, s->comm, s->stream);
+        if (r == 0) r = api->Recv(from_up, bytes, NCCL_CHAR, up2, s->comm, s->stream);
+        if (r != 0) { api->GroupEnd(); return nccl_fail(api, r, "ncclSend/Recv (IPC handles)"); }
+        r = api->GroupEnd();
+        if (r != 0) return nccl_fail(api, r, "ncclGroupEnd (IPC handles)");
+        FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+        return FDTD_OK;
+    };
+    boot.all_min = [](void* ctx, int* value) -> fdtd_status_t {
+        Solver* s = static_cast<Solver*>(ctx);
+        int* d = nullptr;
+        FDTD_CUDA_TRY(cudaMalloc(&d, sizeof(int)));
+        FDTD_CUDA_TRY(cudaMemcpy(d, value, sizeof(int), cudaMemcpyHostToDevice));
+        nccl_result_t r = s->nccl->AllReduce(d, d, 1, NCCL_INT32, NCCL_MIN, s->comm, s->stream);
+        if (r != 0) { cudaFree(d); return nccl_fail(s->nccl, r, "ncclAllReduce"); }
+        FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+        FDTD_CUDA_TRY(cudaMemcpy(value, d, sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        return FDTD_OK;
+    };
+    return peer_ring_init_ipc(s, boot);
 }
 
 void nccl_destroy(Solver* s) {
+    peer_ring_destroy(s);
     if (s->comm && s->nccl) s->nccl->CommDestroy(s->comm);
     s->comm = nullptr;
 }

@@ -1,6 +1,7 @@
 // solver.h -- host-side state of one fdtd_solver_t (one GPU, one z-slab).
 #pragma once
 
+#include <cuda.h>   // CUtensorMap (driver entry points are fetched at run time, nothing links against libcuda)
 #include <cuda_runtime.h>
 
 #include <string>
@@ -12,9 +13,31 @@
 namespace fdtd_b200 {
 
 struct NcclApi;   // dlopen'ed libnccl entry points (nccl_ring.cu)
+struct PeerRing;  // peer-mapped ghost planes + sequence flags (peer_ring.cu)
+
+// flag words of one rank (device memory, written by the neighbours' copy engines)
+enum { PEER_F_READY_FROM_DOWN = 0, PEER_F_READY_FROM_UP = 1, PEER_F_DATA_FROM_DOWN = 2, PEER_F_DATA_FROM_UP = 3,
+       PEER_F_ERR = 4, PEER_F_STAGE = 8, PEER_STAGE_SLOTS = 8, PEER_FLAG_WORDS = 64 };
+
+// Environment switches, read ONCE when the solver is created (tools/sweep.py, tools/mgpu_probe.py and the tests set
+// them before constructing a solver).  Defaults are the measured best on B200 (profiles/).
+struct Tunables {
+    int fused_variant = -1;   // FDTD_B200_FUSED_VARIANT: one-step fused pass variant (-1: per-dtype default)
+    int fused_kc = 0;         // FDTD_B200_FUSED_KC: planes per CTA chunk (0: chosen by the host)
+    int t2_variant = 0;       // FDTD_B200_T2_VARIANT
+    int t2_strip = 0;         // FDTD_B200_T2_STRIP: tile columns per strip (0: row-major tile ids)
+    int st_cs = 1;            // FDTD_B200_ST_CS: streaming output stores (profiles/stcs_r01.jsonl)
+    int tma_l2 = 256;         // FDTD_B200_TMA_L2: L2 promotion of the tensor maps (0, 64, 128, 256)
+    bool no_tma = false;      // FDTD_B200_NO_TMA
+    bool no_t2 = false;       // FDTD_B200_NO_T2
+    bool no_lazy = false;     // FDTD_B200_NO_LAZY
+    int mgpu_debug = 0;       // FDTD_B200_MGPU_DEBUG (timing experiments, tools/mgpu_probe.py)
+    bool pml_t2_f32 = false;  // FDTD_B200_PML_T2_F32
+};
 
 struct Solver {
     fdtd_config_t cfg{};
+    Tunables tun{};
     int device = 0;
     int dtype = FDTD_F64;
     size_t esz = 8;
@@ -73,9 +96,21 @@ struct Solver {
     void* d_stage = nullptr;
     size_t stage_bytes = 0;
 
-    // NCCL ring
+    // NCCL ring (bootstrap + fallback transport) and the copy-engine ring over peer-mapped memory (default transport)
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
+    PeerRing* peer = nullptr;
+    std::string peer_note;         // why the peer transport is not in use (diagnostics)
+    bool halo_in_kernel = true;    // T2 pass: the CTAs that read ghost planes wait for the halo themselves (peer transport only)
+
+    // per-solver launch configuration caches (one cudaFuncSetAttribute per kernel and device context)
+    unsigned configured = 0;       // bit per kernel family
+    // per-pass timeline (fdtd_timeline_enable): events pass start / exchange start / exchange end / pass end
+    std::vector<cudaEvent_t> tl_events;
+    int tl_cap = 0, tl_n = 0;
+    // tensor maps of the six E/B arrays per generation (T2 pass), encoded once
+    CUtensorMap tmaps[2][6];
+    int tmaps_by[2] = {0, 0};      // box rows the cached maps were encoded for (0: not encoded, -1: encoding failed)
 
     int64_t launches = 0;
     int64_t steps_done = 0;
@@ -101,7 +136,29 @@ fdtd_status_t nccl_init(Solver* s, const void* id, size_t bytes);
 void nccl_destroy(Solver* s);
 // Grouped ring exchange of whole planes.  Each entry: send `bytes` from `send` to `peer_send`,
 // receive `bytes` into `recv` from `peer_recv`.
-struct PlaneXfer { const void* send; int peer_send; void* recv; int peer_recv; size_t bytes; };
+// (push view of the same entry, used by the peer transport: the planes go to the upper / lower neighbour's array
+// (comp, gen), plane `dst_plane` in the RECEIVER's numbering: -2, -1 = its bottom ghosts, 0, 1 = its top ghosts
+// nk_peer, nk_peer + 1)
+struct PlaneXfer {
+    const void* send; int peer_send; void* recv; int peer_recv; size_t bytes;
+    int to_upper, comp, gen, dst_plane;
+};
 fdtd_status_t nccl_exchange(Solver* s, const PlaneXfer* x, int n, cudaStream_t stream);
+
+// peer_ring.cu
+struct PeerBootstrap {
+    void* ctx;
+    // send `bytes` from `send` to ranks up and down; receive from `down` into from_down and from `up` into from_up
+    fdtd_status_t (*exchange)(void* ctx, const void* send, int up, int down, void* from_down, int down2, void* from_up, int up2, size_t bytes);
+    fdtd_status_t (*all_min)(void* ctx, int* value);   // min over all ranks
+};
+fdtd_status_t peer_ring_init_ipc(Solver* s, const PeerBootstrap& boot);
+fdtd_status_t peer_ring_init_local(Solver** all, int n);
+void peer_ring_destroy(Solver* s);
+fdtd_status_t peer_exchange(Solver* s, const PlaneXfer* x, int n, cudaStream_t q, bool wait_data, cudaEvent_t ev_start, cudaEvent_t ev_end);
+fdtd_status_t peer_wait_data(Solver* s, cudaStream_t q);
+const unsigned* peer_data_flags(const Solver* s);   // [0] from the lower neighbour, [1] from the upper neighbour
+unsigned* peer_error_word(const Solver* s);
+unsigned peer_last_seq(const Solver* s);
 
 }  // namespace fdtd_b200

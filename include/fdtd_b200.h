@@ -111,6 +111,9 @@ typedef struct fdtd_info {
     int32_t temporal;          /* 1 if fdtd_step(n >= 2) pairs steps into the temporally blocked two-step pass */
     int64_t passes_t2;         /* two-step passes run so far (each advances 2 steps) */
     int64_t kernel_ns;         /* reserved */
+    int32_t transport;         /* halo transport of a multi-rank solver: 0 none (single GPU / not initialised), 1 NCCL send/recv,
+                                  2 copy engines into peer-mapped ghost planes (CUDA IPC or in-process peer access) */
+    int32_t halo_in_kernel;    /* 1: the two-step pass waits for the halo inside the kernel (one launch per pass per rank) */
 } fdtd_info_t;
 
 /* ---- life cycle --------------------------------------------------------- */
@@ -183,7 +186,11 @@ fdtd_status_t fdtd_clear_source(fdtd_solver_t* s);
 fdtd_status_t fdtd_sync(fdtd_solver_t* s);
 
 /* Zero-copy access for CUDA-aware callers: device pointer to element (0,0,k_begin) of `component`
- * (row pitch and plane stride in fdtd_info_t).  Flushes deferred work first. */
+ * (row pitch and plane stride in fdtd_info_t).  Flushes deferred work first.
+ * VALIDITY: E and B are double-buffered by the fused passes, so the pointer addresses the live generation only until
+ * the next fdtd_step / fdtd_update_fields / fdtd_zeroed_currents call on this solver; fetch it again after stepping.
+ * The solver assumes the caller may write through it (ghost planes and the J bounding box are invalidated at call
+ * time only). */
 fdtd_status_t fdtd_device_ptr(fdtd_solver_t* s, int component, void** dptr);
 
 /* ---- introspection / measurement --------------------------------------- */
@@ -194,13 +201,36 @@ fdtd_status_t fdtd_timer_stop(fdtd_solver_t* s, double* elapsed_ms);
 /* The solver's cudaStream_t (as void*), for callers that want to record their own events. */
 fdtd_status_t fdtd_get_stream(fdtd_solver_t* s, void** stream);
 
-/* ---- multi-GPU: one process per GPU, z-slab ring with one-plane halos ----
- * (the reference's only distributed design is coarray/fdtd.F90:85-102,149-164) */
+/* ---- multi-GPU: z-slab ring (the reference's only distributed design is coarray/fdtd.F90:85-102,149-164) ----
+ *
+ * COLLECTIVE CALLS.  On a multi-rank solver every call that steps, or that reads or writes a B component
+ * (fdtd_step, fdtd_update_fields, fdtd_sync, fdtd_download / fdtd_gather / fdtd_read_slice / fdtd_upload / fdtd_scatter /
+ * fdtd_device_ptr of Bx, By, Bz), may run the deferred B half step, which needs the Ex, Ey ring exchange: ALL ranks
+ * must make the same sequence of such calls (fdtd_read_slice with axis 2 included -- ranks that do not own the plane
+ * take part in the exchange and copy nothing).  J writes (fdtd_upload / fdtd_scatter of Jx..Jz, fdtd_set_source) must
+ * also be issued identically on all ranks, with GLOBAL index lists / boxes: each rank tracks the bounding box of the
+ * non-zero currents on the host, and the two-step pass re-computes its neighbours' boundary planes from the exchanged
+ * J planes under that same box.
+ *
+ * TRANSPORT.  Default: every rank pushes its boundary planes into the neighbours' ghost planes with the copy engines
+ * over NVLink (cudaMemcpyAsync into peer-mapped memory, 32-bit sequence flags for the hand-off; csrc/peer_ring.cu) --
+ * no kernel of anybody's runs on an SM, and the two-step pass waits for the halo inside the kernel.  One process per
+ * GPU: fdtd_comm_init() (NCCL carries the CUDA IPC handles and stays the fallback; FDTD_B200_TRANSPORT=nccl forces it).
+ * One process driving several GPUs: fdtd_comm_init_local(). */
 #define FDTD_NCCL_UNIQUE_ID_BYTES 128
 /* Rank 0 calls this and ships the bytes to the other ranks (torch.distributed broadcast, a file, ...). */
 fdtd_status_t fdtd_nccl_unique_id(void* id_out, size_t capacity);
 /* All ranks call this with the same id; uses cfg.rank / cfg.nranks given at creation. */
 fdtd_status_t fdtd_comm_init(fdtd_solver_t* s, const void* id, size_t id_bytes);
+/* One process, n GPUs: solvers[r] was created with cfg.rank = r, cfg.nranks = n, cfg.device = its GPU.  Links the
+ * ring through plain peer access (no NCCL).  The caller then issues every collective call on all n handles from one
+ * host thread, in any order (all calls are asynchronous; nothing blocks on a neighbour on the host). */
+fdtd_status_t fdtd_comm_init_local(fdtd_solver_t** solvers, int n);
+/* Per-pass timeline of the overlapped passes: after enable, the next max_passes passes record four CUDA events each
+ * (pass start, halo copies start, halo copies issued/done on this rank's side, pass end); read returns their times in
+ * ms relative to the first pass start, 4 doubles per pass. */
+fdtd_status_t fdtd_timeline_enable(fdtd_solver_t* s, int max_passes);
+fdtd_status_t fdtd_timeline_read(fdtd_solver_t* s, double* ms, int capacity_passes, int* n_passes);
 /* Plane range owned by `rank` of `nranks` for a grid with Nk planes (remainder spread over low ranks). */
 void fdtd_slab_range(int Nk, int rank, int nranks, int* k_begin, int* k_end);
 

@@ -19,7 +19,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle.pyoracle import (BX, BY, BZ, C, COMPONENTS, EX, EY, EZ, JX, JY, JZ, PI, Reference,  # noqa: E402
-                             run_sample, sample_params)
+                             ReferenceKokkos, have_reference_kokkos, run_sample, sample_params)
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -49,6 +49,28 @@ def random_case(name, Ni, Nj, Nk, d, dt, steps, seed, pml):
     meta = dict(Ni=Ni, Nj=Nj, Nk=Nk, dx=d[0], dy=d[1], dz=d[2], dt=dt, steps=list(steps), seed=seed,
                 pml_percent=pml, rng="numpy default_rng(seed).uniform(-1,1) EX..BZ then J (Jx=Jy=Jz)",
                 source="oracle/_ref/libfdtd_ref.so (FDTD_openmp, g++ -O3 -fopenmp -DNDEBUG, 1 thread)")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), **snaps)
+    print("wrote", name, {k: float(np.abs(v).max()) for k, v in list(snaps.items())[:2]})
+
+
+def kokkos_case(name, Ni, Nj, Nk, d, dt, steps, seed, pml):
+    """Distinct Jx / Jy / Jz through the real Kokkos path (kokkos_functors.h:81-89): pins the oracle's J_KOKKOS mode.
+    (Kokkos is initialised with whatever OMP_NUM_THREADS is in effect; __main__ re-executes itself with
+    OMP_NUM_THREADS=1 for these cases.)"""
+    r = ReferenceKokkos(Ni, Nj, Nk, d[0], d[1], d[2], dt, pml_percent=pml)
+    init = seeded_fields(seed, (Nk, Nj, Ni), same_j=False)
+    for c in range(9):
+        r.field(c)[...] = init[c]
+    snaps = {}
+    done = 0
+    for s in steps:
+        r.step(s - done)
+        done = s
+        for c in range(6):
+            snaps[f"{COMPONENTS[c]}_step{s}"] = r.field(c).copy()
+    meta = dict(Ni=Ni, Nj=Nj, Nk=Nk, dx=d[0], dy=d[1], dz=d[2], dt=dt, steps=list(steps), seed=seed,
+                pml_percent=pml, rng="numpy default_rng(seed).uniform(-1,1) EX..BZ then Jx, Jy, Jz (distinct)",
+                source=f"oracle/_ref/libfdtd_ref_kokkos.so (FDTD_kokkos, Kokkos OpenMP backend, g++ -O3 -fopenmp -DNDEBUG, {ReferenceKokkos.threads()} thread(s))")
     np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), **snaps)
     print("wrote", name, {k: float(np.abs(v).max()) for k, v in list(snaps.items())[:2]})
 
@@ -136,6 +158,17 @@ def convergence_case(name):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--kokkos-only" in sys.argv or have_reference_kokkos():
+        if os.environ.get("OMP_NUM_THREADS") != "1":   # pin the Kokkos goldens at one thread (G4), in a fresh process
+            import subprocess
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "--kokkos-only"], env=dict(os.environ, OMP_NUM_THREADS="1"))
+        else:
+            kokkos_case("random_periodic_kokkos_16x12x10", 16, 12, 10, (C, 1.25 * C, 0.8 * C), 0.2, (1, 10, 30), 45, None)
+            # (no Kokkos PML golden: FDTD_PML_kokkos.cpp:26-45 allocates the split fields WithoutInitializing and never
+            # zero-fills them, SURVEY.md G5 -- the run produced NaN here; the OpenMP PML is the PML oracle)
+            sys.exit(0)
+    if "--kokkos-only" in sys.argv:
+        sys.exit(0)
     random_case("random_periodic_16x12x10", 16, 12, 10, (C, 1.25 * C, 0.8 * C), 0.2, (1, 10, 50), 42, None)
     random_case("random_periodic_33x7x5", 33, 7, 5, (C, C, C), 0.2, (3, 20), 7, None)
     random_case("random_pml_20x16x12", 20, 16, 12, (C, 1.25 * C, 0.8 * C), 0.2, (1, 10, 40), 43, 0.2)

@@ -4,6 +4,8 @@
                   (oracle/fdtd_oracle.c).
 * ``Reference`` -- oracle/_ref/libfdtd_ref.so, the UNMODIFIED reference sources
                   (src/FDTD/FDTD.cpp, src/FDTD/FDTD_PML.cpp) behind oracle/ref_shim.cpp.
+* ``ReferenceKokkos`` -- oracle/_ref/libfdtd_ref_kokkos.so, the UNMODIFIED Kokkos-OpenMP path
+                  (src/FDTD_kokkos/*.cpp + the vendored Kokkos) behind oracle/ref_kokkos_shim.cpp.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this module.  Nothing under fdtd_method_b200/ does.
@@ -19,6 +21,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libfdtd_ref.so")
+REF_KOKKOS_SO = os.path.join(HERE, "_ref", "libfdtd_ref_kokkos.so")
 
 # include/Enums.h:5
 EX, EY, EZ, BX, BY, BZ, JX, JY, JZ = range(9)
@@ -39,10 +42,16 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if os.path.isdir("/root/reference/src/FDTD") and (force or not os.path.exists(REF_SO)):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+    if os.path.isdir("/root/reference/3rdparty/kokkos/core") and (force or not os.path.exists(REF_KOKKOS_SO)):
+        subprocess.call(["make", "-s", "-C", HERE, "ref_kokkos"])   # needs cmake; optional (tests skip without it)
 
 
 def have_reference() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_reference_kokkos() -> bool:
+    return os.path.exists(REF_KOKKOS_SO)
 
 
 class Oracle:
@@ -203,6 +212,75 @@ class Reference:
     def close(self):
         if self._h:
             self.lib().ref_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ReferenceKokkos:
+    """The real reference's Kokkos-OpenMP path (FDTD_kokkos::FDTD / FDTD_PML) through oracle/ref_kokkos_shim.cpp.
+    Distinct Jx / Jy / Jz feed Ex / Ey / Ez (kokkos_functors.h:81-89) -- what the oracle's J_KOKKOS mode restates.
+    Kokkos is initialised once per process with the OpenMP thread count in effect at the first create()."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            build()
+            if not os.path.exists(REF_KOKKOS_SO):
+                raise FileNotFoundError(REF_KOKKOS_SO)
+            L = ctypes.CDLL(REF_KOKKOS_SO)
+            L.refk_create.restype = ctypes.c_void_p
+            L.refk_create.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double] * 11
+            L.refk_field.restype = ctypes.c_void_p
+            L.refk_field.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            for n in ("refk_update_fields", "refk_zeroed_currents", "refk_destroy"):
+                getattr(L, n).restype = None
+                getattr(L, n).argtypes = [ctypes.c_void_p]
+            L.refk_step.restype = None
+            L.refk_step.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            L.refk_threads.restype = ctypes.c_int
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, Ni, Nj, Nk, dx, dy, dz, dt, pml_percent=None, box=None):
+        L = self.lib()
+        self.shape = (Nk, Nj, Ni)
+        ax, bx, ay, by, az, bz = box if box is not None else (0.0, Ni * dx, 0.0, Nj * dy, 0.0, Nk * dz)
+        self._h = L.refk_create(Ni, Nj, Nk, ax, bx, ay, by, az, bz, dx, dy, dz, dt,
+                                -1.0 if pml_percent is None else float(pml_percent))
+        if not self._h:
+            raise ValueError("ERROR: invalid parameters")
+
+    def field(self, comp) -> np.ndarray:
+        ptr = self.lib().refk_field(self._h, comp)
+        if not ptr:
+            raise RuntimeError("ERROR: Invalid field component")
+        n = self.shape[0] * self.shape[1] * self.shape[2]
+        buf = (ctypes.c_double * n).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float64).reshape(self.shape)
+
+    def update_fields(self):
+        self.lib().refk_update_fields(self._h)
+
+    def step(self, n):
+        self.lib().refk_step(self._h, n)
+
+    def zeroed_currents(self):
+        self.lib().refk_zeroed_currents(self._h)
+
+    @classmethod
+    def threads(cls):
+        return cls.lib().refk_threads()
+
+    def close(self):
+        if self._h:
+            self.lib().refk_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -448,7 +448,7 @@ def test_temporal_blocking_bit_exact(shape, steps, dtype):
     assert_bit_equal(o, g, what=f"T2 second batch {shape}")
 
 
-@pytest.mark.parametrize("variant", range(9))
+@pytest.mark.parametrize("variant", range(3))
 def test_temporal_blocking_variants(variant, monkeypatch):
     monkeypatch.setenv("FDTD_B200_T2_VARIANT", str(variant))
     Ni, Nj, Nk = 68, 37, 21
@@ -489,3 +489,96 @@ def test_temporal_blocking_device_source(n, active, steps):
         o.update_fields()
     g.step(steps)
     assert_bit_equal(o, g, comps=range(9), what=f"T2 device source active={active} steps={steps}")
+
+
+# ---- the benchmarked flavours of the T2 pass: TMA-fed tiles, both storage types (missing #3) -------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("currents", ["none", "box"])
+@pytest.mark.parametrize("shape,steps", [((128, 48, 12), 6), ((192, 40, 9), 5), ((250, 30, 7), 4), ((252, 30, 7), 4),
+                                         ((256, 64, 6), 4), ((136, 28, 20), 7)])
+def test_temporal_blocking_tma_tiles(shape, steps, dtype, currents):
+    """Grids wide enough that interior tiles take the TMA ring (footprint 64 cells x 16 rows without a periodic wrap:
+    Ni >= 122, Nj >= 26) while edge tiles keep the per-thread cp.async ring -- fp64 (64-cell boxes) and fp32 (68-cell
+    boxes starting 2 cells early).  `currents` = "none": every tile runs the J-free flavours; "box": J is non-zero on a
+    small box only, so the tiles that meet it run the J flavour next to TMA tiles.  Ni = 250 / 252: the last tile column
+    wraps (Ni is not a multiple of the 60-cell tile); fp32 needs Ni % 4 == 0 for the fused passes (250 -> sweep kernels)."""
+    Ni, Nj, Nk = shape
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), dtype=dtype)
+    f = seeded_fields(57, (Nk, Nj, Ni), dtype=dtype, same_j=False)
+    load_both(o, g, f, comps=range(6))
+    if currents == "box":
+        idx = np.array([i + j * Ni + k * Ni * Nj for k in (1, 2) for j in (20, 21, 22) for i in range(70, 76)])
+        for c in (6, 7, 8):
+            vals = f[c].reshape(-1)[idx]
+            g.scatter(c, idx, vals)
+            o.field(c).reshape(-1)[idx] = vals
+    o.step(steps); g.step(steps)
+    if g.info().fused:
+        assert g.info().passes_t2 == steps // 2
+    assert_bit_equal(o, g, what=f"T2 TMA tiles {shape} {np.dtype(dtype).name} J={currents}")
+    o.step(3); g.step(3)
+    assert_bit_equal(o, g, what=f"T2 TMA tiles, second batch {shape}")
+
+
+def _checker(Ni, Nj, Nk, d, dt):
+    """The real reference when oracle/_ref travelled to this box, else the C restatement in the same J semantics."""
+    from oracle.pyoracle import Reference, have_reference
+    if have_reference():
+        return Reference(Ni, Nj, Nk, d[0], d[1], d[2], dt), "reference"
+    return Oracle(Ni, Nj, Nk, d[0], d[1], d[2], dt, j_mode=J_OPENMP), "oracle"
+
+
+@pytest.mark.parametrize("shape,steps", [((256, 256, 256), 10), ((512, 512, 64), 4)])
+def test_baseline_size_against_reference(shape, steps):
+    """BASELINE sizes against the reference itself (FDTD_openmp::FDTD, src/FDTD/FDTD.cpp:153-157, through oracle/_ref):
+    256^3 x 10 steps (configs[1]) and a 64-plane slab of the 512^3 bench grid x 4 steps (configs[2]: random E/B seed 42,
+    the sample's point source active every step), bit for bit."""
+    Ni, Nj, Nk = shape
+    d = (C, C, C)
+    ref, kind = _checker(Ni, Nj, Nk, d, 0.2)
+    g = fb.FDTD(params(Ni, Nj, Nk), 0.2, j_openmp_quirk=True)
+    rng = np.random.default_rng(42)
+    for c in range(6):
+        a = rng.uniform(-1, 1, size=(Nk, Nj, Ni))
+        ref.field(c)[...] = a
+        g.upload(c, a)
+    import math
+    PI, T, Tx = 3.14159265358, 8.0, 4.0 * C
+    lo = [N // 2 - 1 for N in (Ni, Nj, Nk)]
+    hi = [N // 2 + 1 for N in (Ni, Nj, Nk)]
+    w = [[math.pow(math.cos(2.0 * PI * (float(i - N // 2) * C) / Tx), 2.0) for i in range(l, h)] for l, h, N in zip(lo, hi, (Ni, Nj, Nk))]
+    amp = [math.sin(2.0 * PI * (float(t + 1) * 0.2) / T) for t in range(steps)]
+    g.set_source(lo, hi, w[0], w[1], w[2], amp)
+    g.step(steps)
+    for t in range(steps):
+        for k in range(lo[2], hi[2]):
+            for j in range(lo[1], hi[1]):
+                for i in range(lo[0], hi[0]):
+                    v = ((amp[t] * w[0][i - lo[0]]) * w[1][j - lo[1]]) * w[2][k - lo[2]]
+                    for c in (6, 7, 8):
+                        ref.field(c)[k, j, i] = v
+        ref.update_fields()
+    assert g.info().passes_t2 == steps // 2
+    for c in range(6):
+        assert np.array_equal(g.download(c), ref.field(c)), f"{shape} component {c} differs from the {kind}"
+    ref.close()
+
+
+def test_golden_kokkos_distinct_currents(golden_dir):
+    """Committed outputs of the real FDTD_kokkos::FDTD with distinct Jx / Jy / Jz (kokkos_functors.h:81-89): the GPU
+    solver's default J semantics, no oracle in the loop."""
+    z = np.load(os.path.join(golden_dir, "random_periodic_kokkos_16x12x10.npz"))
+    m = json.loads(str(z["meta"]))
+    Ni, Nj, Nk = m["Ni"], m["Nj"], m["Nk"]
+    for fusion in (True, False):
+        g = fb.FDTD(fb.Parameters(Ni, Nj, Nk, 0, Ni * m["dx"], 0, Nj * m["dy"], 0, Nk * m["dz"], m["dx"], m["dy"], m["dz"]), m["dt"], fusion=fusion)
+        f = seeded_fields(m["seed"], (Nk, Nj, Ni), same_j=False)
+        for c in range(9):
+            g.upload(c, f[c])
+        done = 0
+        for s in m["steps"]:
+            g.step(s - done)
+            done = s
+            for c, nm in enumerate(["EX", "EY", "EZ", "BX", "BY", "BZ"]):
+                assert np.array_equal(g.download(c), z[f"{nm}_step{s}"]), f"{nm} step {s} fusion={fusion}"
+        g.close()
