@@ -10,8 +10,14 @@ initial E/B (seed 42) plus the reference sample's point current source kept acti
 the same 512^3 block PER GPU, z-slab partitioned (weak scaling, 512 x 512 x 512*N), one process per GPU,
 halo planes over NCCL send/recv.  One JSON line on stdout (rank 0).
 
+Timing: after W warm-up steps, R (--reps, default 5) blocks of K steps are timed one by one with CUDA events on the
+solver's stream; every block ends with fdtd_flush(), so the closing B half step of its last update_fields() is INSIDE
+the timed region.  `ms_per_step` / `value` are the median block (max over ranks per block); all blocks are listed.
+
 `--impl reference` times the reference's own CPU implementation (oracle/_ref/libfdtd_ref.so = the unmodified
-src/FDTD/FDTD.cpp compiled by oracle/Makefile; the C oracle port when that file is absent) on the host cores.
+src/FDTD/FDTD.cpp compiled by oracle/Makefile; the C oracle port when that file is absent) on the host cores, each leg in
+a child process started with OMP_NUM_THREADS / OMP_PROC_BIND=spread / OMP_PLACES=threads: plain
+C++/OpenMP at all threads (the line's value), at 1 thread, and the Kokkos-OpenMP path (oracle/_ref/libfdtd_ref_kokkos.so).
 """
 from __future__ import annotations
 
@@ -45,13 +51,51 @@ def measured_peak():
 
 
 def ncu_traffic(dtype, n):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture, or None."""
+    """(per-launch DRAM bytes of the dominant kernel, where the number comes from): read from the committed ncu
+    --set full capture (profiles/ncu_traffic.json, which names the commit and capture it was taken from) -- DRAM
+    counters cannot be read live outside a profiler."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             d = json.load(fh)
-        return d.get(f"{dtype}_{n}", {}).get("dram_bytes_per_launch")
+        e = d.get(f"{dtype}_{n}", {})
+        return e.get("dram_bytes_per_launch"), f"profiles/ncu_traffic.json: {e.get('source', d.get('source', 'ncu --set full'))}"
     except Exception:
-        return None
+        return None, None
+
+
+def verify_against_cpu(fb, n, dtype, device):
+    """4 steps of an n x n x 64 slab of the bench workload (random E/B seed 42 + the sample source) on the GPU against the
+    CPU checker, bit for bit.  The checker is test infrastructure (oracle/): it verifies, it is never what is timed."""
+    from oracle import pyoracle
+    nk, steps = 64, 4
+    p = fb.Parameters(n, n, nk, -n / 2 * C, n / 2 * C, -n / 2 * C, n / 2 * C, -nk / 2 * C, nk / 2 * C, C, C, C)
+    g = fb.FDTD(p, 0.2, dtype=dtype, device=device, j_openmp_quirk=True)
+    if dtype == np.float64 and pyoracle.have_reference():
+        chk, kind = pyoracle.Reference(n, n, nk, C, C, C, 0.2), "reference (oracle/_ref, FDTD_openmp::FDTD)"
+    else:
+        chk, kind = pyoracle.Oracle(n, n, nk, C, C, C, 0.2, dtype=dtype, j_mode=pyoracle.J_OPENMP), "oracle port (oracle/liboracle.so)"
+    rng = np.random.default_rng(42)
+    for c in range(6):
+        f = rng.uniform(-1, 1, size=(nk, n, n)).astype(dtype)
+        chk.field(c)[...] = f
+        g.upload(c, f)
+    lo, hi, w, amp = sample_source_tables((n, n, nk), steps)
+    g.set_source(lo, hi, w[0], w[1], w[2], amp)
+    g.step(steps)
+    for t in range(steps):
+        for kk in range(lo[2], hi[2]):
+            for jj in range(lo[1], hi[1]):
+                for ii in range(lo[0], hi[0]):
+                    v = ((amp[t] * w[0][ii - lo[0]]) * w[1][jj - lo[1]]) * w[2][kk - lo[2]]
+                    for c in (6, 7, 8):
+                        chk.field(c)[kk, jj, ii] = v
+        chk.update_fields()
+    worst = 0.0
+    for c in range(6):
+        worst = max(worst, float(np.abs(g.download(c).astype(np.float64) - chk.field(c).astype(np.float64)).max()))
+    passes = int(g.info().passes_t2)
+    g.close(); chk.close()
+    return {"grid": [n, n, nk], "steps": steps, "checker": kind, "max_abs_diff": worst, "bit_exact": worst == 0.0, "t2_passes": passes}
 
 
 def sample_source_tables(n_global, nsteps):
@@ -101,7 +145,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def result(self):
         self.stop_flag = True
@@ -114,44 +158,48 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------------
 # CPU side: the reference's own implementation on the host cores
 # --------------------------------------------------------------------------------------------------------
-def cpu_solver(shape, pml):
-    """(solver, kind): the real reference when oracle/_ref travelled here, else the C oracle port."""
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_leg_main(a):
+    """Child process of one CPU leg (bench.py --cpu-leg openmp|kokkos ...): started with the OpenMP environment already
+    in place, so libgomp reads OMP_NUM_THREADS / OMP_PROC_BIND / OMP_PLACES when it loads.  Prints one JSON object."""
     from oracle import pyoracle
-    Ni, Nj, Nk = shape
-    if pyoracle.have_reference():
-        # all the host threads: torchrun exports OMP_NUM_THREADS=1 to its children, which would silently make this a
-        # single-thread baseline at N > 1
-        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        if pyoracle.Reference.max_threads() < ncpu:
-            pyoracle.Reference.set_threads(ncpu)
-        return pyoracle.Reference(Ni, Nj, Nk, C, C, C, 0.2, pml_percent=pml), "reference", pyoracle.Reference.max_threads()
-    return pyoracle.Oracle(Ni, Nj, Nk, C, C, C, 0.2, pml_percent=pml), "port", (os.cpu_count() or 1)
-
-
-def time_cpu(n, steps, warmup, pml=None, budget_s=25.0):
-    """Gcell-updates/s of the CPU path on a bounded sample: the same 512x512 planes, fewer of them."""
-    nk = n
-    solver, kind, cores = cpu_solver((n, n, 32), pml)
+    n, nk = a.n, a.nk
+    pml = 0.0625 if a.workload == "pml" else None
+    if a.cpu_leg == "kokkos":
+        solver, kind = pyoracle.ReferenceKokkos(n, n, nk, C, C, C, 0.2, pml_percent=pml), "reference"
+        threads = pyoracle.ReferenceKokkos.threads()
+        what = "FDTD_kokkos::FDTD, Kokkos OpenMP backend (oracle/_ref/libfdtd_ref_kokkos.so)"
+    elif pyoracle.have_reference():
+        solver, kind = pyoracle.Reference(n, n, nk, C, C, C, 0.2, pml_percent=pml), "reference"
+        threads = pyoracle.Reference.max_threads()
+        what = "FDTD_openmp::FDTD (oracle/_ref/libfdtd_ref.so)"
+    else:
+        solver, kind = pyoracle.Oracle(n, n, nk, C, C, C, 0.2, pml_percent=pml), "port"
+        threads = int(os.environ.get("OMP_NUM_THREADS", "1"))
+        what = "C oracle port (oracle/liboracle.so)"
     rng = np.random.default_rng(42)
     for c in range(6):
-        solver.field(c)[...] = rng.uniform(-1, 1, size=(32, n, n))
-    solver.update_fields()
-    t0 = time.perf_counter()
-    solver.update_fields()
-    per_plane = (time.perf_counter() - t0) / 32.0
-    solver.close()
-    # planes such that (warmup + steps) steps take about `budget_s`
-    nk = int(budget_s / max(per_plane * (steps + warmup), 1e-9))
-    nk = max(32, min(n, (nk // 32) * 32))
-    solver, kind, cores = cpu_solver((n, n, nk), pml)
-    for c in range(6):
-        a = solver.field(c)
+        f = solver.field(c)
         for k0 in range(0, nk, 32):
-            a[k0:k0 + 32] = rng.uniform(-1, 1, size=(min(32, nk - k0), n, n))
-    lo, hi, w, amp = sample_source_tables((n, n, nk), steps + warmup)
+            f[k0:k0 + 32] = rng.uniform(-1, 1, size=f[k0:k0 + 32].shape)
+    total = a.warmup + a.steps * a.reps
+    lo, hi, w, amp = sample_source_tables((n, n, nk), total)
     jx, jy, jz = solver.field(6), solver.field(7), solver.field(8)
 
-    def one(t):
+    def one(t):   # the reference caller's per-step J writes (sample.cpp:66-81), then update_fields()
         for kk in range(lo[2], hi[2]):
             for jj in range(lo[1], hi[1]):
                 for ii in range(lo[0], hi[0]):
@@ -159,33 +207,88 @@ def time_cpu(n, steps, warmup, pml=None, budget_s=25.0):
                     jx[kk, jj, ii] = v; jy[kk, jj, ii] = v; jz[kk, jj, ii] = v
         solver.update_fields()
 
-    for t in range(warmup):
-        one(t)
-    t0 = time.perf_counter()
-    for t in range(steps):
-        one(warmup + t)
-    dt = time.perf_counter() - t0
+    t = 0
+    for _ in range(a.warmup):
+        one(t); t += 1
+    blocks = []
+    for _ in range(a.reps):
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            one(t); t += 1
+        blocks.append((time.perf_counter() - t0) / a.steps)
     solver.close()
-    cells = n * n * nk
-    return dict(value=cells * steps / dt / 1e9, unit="Gcell-updates/s", cores=cores, kind=kind,
-                sample=f"{n}x{n}x{nk} fp64 periodic slab of the {n}^3 workload, {steps} steps after {warmup} warm-up, "
-                       f"{'FDTD_openmp::FDTD (oracle/_ref)' if kind == 'reference' else 'C oracle port (oracle/liboracle.so)'}, "
-                       f"OMP threads={cores}",
-                ms_per_step=dt / steps * 1e3, cells=cells)
+    med = float(np.median(blocks))
+    emit(dict(ok=True, kind=kind, what=what, threads=threads, n=n, nk=nk, steps=a.steps, reps=a.reps, warmup=a.warmup,
+                          s_per_step=med, s_per_step_all=blocks, cells=n * n * nk, value=n * n * nk / med / 1e9))
+
+
+def cpu_leg(leg, threads, n, nk, steps, warmup, reps, workload="periodic", timeout=300):
+    """Run one CPU leg in a child process with the OpenMP environment of BASELINE.md section 3; returns its JSON dict."""
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="threads")
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-leg", leg, "--n", str(n), "--nk", str(nk), "--steps", str(steps),
+           "--warmup", str(warmup), "--reps", str(reps), "--workload", workload]
+    try:
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return dict(ok=False, error=(r.stderr or r.stdout)[-300:])
+    except Exception as e:
+        return dict(ok=False, error=repr(e))
+
+
+def planes_for_budget(n, per_plane_step_s, steps_total, budget_s):
+    nk = int(budget_s / max(per_plane_step_s * steps_total, 1e-9))
+    return max(32, min(n, (nk // 32) * 32))
+
+
+def cpu_baseline(n, steps, warmup, reps, budget_s, workload="periodic", with_c1=False):
+    """The reference's CPU paths on this box's host cores, on a bounded slab (n x n x nk planes) of the n^3 workload:
+    plain C++/OpenMP at all threads (the headline CPU number), the same at 1 thread, and Kokkos-OpenMP at all threads.
+    Median of `reps` blocks of `steps` steps after `warmup` steps."""
+    ncpu = host_threads()
+    probe = cpu_leg("openmp", ncpu, n, 32, 1, 1, 1, workload)
+    if not probe.get("ok"):
+        raise RuntimeError(f"cpu leg failed: {probe.get('error')}")
+    per_plane = probe["s_per_step"] / 32.0
+    total = warmup + steps * reps
+    nk = planes_for_budget(n, per_plane, total, budget_s * 0.5)
+    main = cpu_leg("openmp", ncpu, n, nk, steps, warmup, reps, workload)
+    if not main.get("ok"):
+        raise RuntimeError(f"cpu leg failed: {main.get('error')}")
+    # 1 thread: ~ncpu x slower per plane -> a thinner slab; Kokkos: the same slab as the OpenMP leg
+    nk1 = planes_for_budget(n, per_plane * ncpu * 0.7, total, budget_s * 0.25)
+    one = cpu_leg("openmp", 1, n, nk1, steps, warmup, reps, workload)
+    from oracle import pyoracle
+    kok = cpu_leg("kokkos", ncpu, n, planes_for_budget(n, per_plane * 1.4, total, budget_s * 0.25), steps, warmup, reps, workload) \
+        if (pyoracle.have_reference_kokkos() and workload == "periodic") else dict(ok=False, error="oracle/_ref/libfdtd_ref_kokkos.so not present")
+    out = dict(value=main["value"], unit="Gcell-updates/s", cores=main["threads"], kind=main["kind"],
+               sample=f"{n}x{n}x{main['nk']} fp64 {workload} slab of the {n}^3 workload (same planes, fewer of them), median of {reps} x {steps} steps "
+                      f"after {warmup} warm-up, {main['what']}, OMP_NUM_THREADS={main['threads']} OMP_PROC_BIND=spread OMP_PLACES=threads",
+               ms_per_step=main["s_per_step"] * 1e3, cells=main["cells"], cpu_model=cpu_model(), nproc=ncpu,
+               build="g++ -O3 -fopenmp -DNDEBUG (the reference's flags, no -march)",
+               one_thread=(dict(value=one["value"], cores=1, sample=f"{n}x{n}x{one['nk']} slab, {one['what']}") if one.get("ok") else dict(value=None, error=one.get("error"))),
+               kokkos_openmp=(dict(value=kok["value"], cores=kok["threads"], sample=f"{n}x{n}x{kok['nk']} slab, {kok['what']}") if kok.get("ok") else dict(value=None, error=kok.get("error"))))
+    if with_c1:
+        # C1, the reference's own perf test at the CI size (`sample 512 25`: zero fields, point source, 25 steps), slab-bounded
+        c1 = cpu_leg("openmp", ncpu, n, planes_for_budget(n, per_plane, 25, 12.0), 25, 0, 1, workload)
+        out["c1_sample_25_steps"] = dict(value=c1.get("value"), sample=f"{n}x{n}x{c1.get('nk')} slab, 25 steps, no warm-up (sample.cpp's timed loop)") if c1.get("ok") else dict(value=None, error=c1.get("error"))
+    return out
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = a.n
-    r = time_cpu(n, a.steps, a.warmup, pml=(0.0625 if a.workload == "pml" else None), budget_s=100.0)
+    r = cpu_baseline(a.n, a.steps, a.warmup, max(a.reps, 3) if a.reps_given else 3, budget_s=90.0, workload=a.workload, with_c1=True)
     line = {
         "impl": "reference", "metric": "Gcell-updates/s (E+B step)", "value": r["value"], "unit": "Gcell-updates/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a, a.gpus, note="CPU arm runs a bounded slab of the same planes"),
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": workload_config(a, a.gpus, note="CPU arm: a bounded slab of the same n x n planes (throughput per cell does not depend on the plane count); "
+                                                    "at N > 1 the GPU arm's grid grows to n x n x n*N while this arm stays on one host"),
+        "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -236,7 +339,7 @@ def run_ours(a):
             idt.copy_(torch.frombuffer(bytearray(fb.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         g.comm_init(bytes(idt.cpu().numpy().tobytes()))
-    info = g.info()
+    info = info2 = g.info()
     nk_local = info.k_end - info.k_begin
     cells_local = n * n * nk_local
     cells_total = n * n * Nk
@@ -258,7 +361,7 @@ def run_ours(a):
         v = t.numpy()
         for k0 in range(0, nk_local, 64):
             v[k0:k0 + 64] = rng.uniform(-1, 1, size=v[k0:k0 + 64].shape)
-    total_steps = a.warmup + a.steps
+    total_steps = a.warmup + a.steps * a.reps
     lo, hi, w, amp = sample_source_tables((n, n, Nk), total_steps + 1)
 
     def barrier():
@@ -266,25 +369,38 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity spot check at the bench shape (rank 0, N = 1): 4 steps of a 64-plane slab of this very workload against
+    # the reference itself (oracle/_ref) or the C oracle, bit for bit, BEFORE anything is timed ---------------------------
+    verify = None
+    if a.verify and world == 1 and a.workload == "periodic":
+        verify = verify_against_cpu(fb, n, dtype, local)
+
     # ---- device-resident leg: inputs already in HBM when the timed region starts --------------------------
     for c in range(6):
         g.upload(c, host[c].numpy())
     g.set_source(lo, hi, w[0], w[1], w[2], amp)
     g.step(a.warmup)
     g.sync()
+    if a.timeline and world > 1:
+        g.timeline_enable(a.reps * (a.steps // 2 + 1))
     barrier()
     launches0 = g.info().launches
     passes0 = g.info().passes_t2
     sampler = ClockSampler(local)
     sampler.start()
-    g.timer_start()
-    g.step(a.steps)
-    ms = g.timer_stop()
+    rep_ms = []
+    for _ in range(a.reps):
+        # one block = K update_fields(); flush() puts the closing B half step inside the timed region
+        g.timer_start()
+        g.step(a.steps)
+        g.flush()
+        rep_ms.append(g.timer_stop())
+        barrier()
     clocks = sampler.result()
-    barrier()
-    launches = g.info().launches - launches0
-    g_passes_t2 = g.info().passes_t2 - passes0
+    launches = (g.info().launches - launches0) // a.reps          # per block
+    g_passes_t2 = (g.info().passes_t2 - passes0) // a.reps
     g.sync()
+    timeline = g.timeline_read().tolist() if (a.timeline and world > 1) else None
 
     # ---- end-to-end leg: HOST buffers in, HOST buffers out, through the public API -------------------------
     # upload the 6 fields from pinned memory, every step write that step's J from the host (the reference
@@ -299,6 +415,7 @@ def run_ours(a):
                          dtype=np.int64)
     wprod = np.array([(w[0][(q % n) - lo[0]], w[1][((q // n) % n) - lo[1]], w[2][(q // (n * n)) - lo[2]]) for q in src_idx])
     e2e_steps = a.steps
+    amp = amp[-(e2e_steps + 1):]
     barrier()
     t0 = time.perf_counter()
     for c in range(0 if a.no_e2e else 6):
@@ -319,13 +436,23 @@ def run_ours(a):
     d2h = field_bytes / e2e_steps + probe_idx.size * W
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------
+    rep_ms_rank = list(rep_ms)
     if world > 1:
-        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(tt[0]), float(tt[1])
+        tt = torch.tensor(rep_ms + [e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)          # per block: the slowest rank
+        rep_ms, e2e_s = [float(v) for v in tt[:-1]], float(tt[-1])
         ll = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(ll, op=dist.ReduceOp.SUM)
         launches = int(ll[0])
+        cm = torch.tensor([clocks.get("sm_mhz") or 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cm, op=dist.ReduceOp.MIN)
+        clocks["sm_mhz_min_over_ranks"] = float(cm[0])
+        if timeline is not None:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"timeline_n{world}_rank{rank}.json"), "w") as fh:
+                json.dump({"rank": rank, "world": world, "columns": ["pass_start_ms", "halo_copies_start_ms", "halo_copies_done_ms", "pass_end_ms"],
+                           "rep_ms_this_rank": rep_ms_rank, "passes": timeline}, fh)
+    ms = float(np.median(rep_ms))
     value = cells_total * a.steps / (ms * 1e-3) / 1e9
     e2e_value = None if a.no_e2e else cells_total * e2e_steps / e2e_s / 1e9
 
@@ -358,8 +485,9 @@ def run_ours(a):
             kernel = ("fused_BE_T2_kernel (one launch = TWO Yee steps of this rank's slab)" if t2 else
                       "fused_BE_kernel (one launch = one Yee step of this rank's slab)" if fused
                       else "sweep_B_kernel + sweep_E_kernel (two launches = one Yee step)")
+        traffic, traffic_src = ncu_traffic(a.dtype, n) if not pml else (None, None)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(a.dtype, n) if not pml else None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "kernel": kernel,
                 "kernel_ms": kernel_ms, "steps_per_launch": steps_per_launch,
@@ -373,19 +501,25 @@ def run_ours(a):
         line = {
             "metric": "Gcell-updates/s (E+B step)", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "reps": a.reps, "rep_ms": rep_ms, "timing": "median of `reps` blocks of `steps` steps, each block timed with CUDA events on the solver's stream "
+                                                        "(max over ranks per block) and closed by fdtd_flush(): the trailing B half step is inside the timed region",
             "scaling": a.scaling, "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": workload_config(a, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": f"upload 6 fields from {'pinned' if pinned else 'PAGEABLE (pin_memory failed)'} host + {e2e_steps} x (scatter J from host, update_fields, gather "
                             f"10x10 Ex probe to host) + download 6 fields, wall clock, max over ranks", "probe_checksum": probe_sum},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "gpu_launches_all_reps": launches * a.reps,
             "roofline": roof,
         }
+        if verify is not None:
+            line["verify"] = verify
+        if world > 1:
+            line["halo"] = {"transport": {0: "none", 1: "nccl send/recv", 2: "copy engines into peer-mapped ghost planes"}[int(info2.transport)],
+                            "wait_in_kernel": bool(info2.halo_in_kernel)}
         if world == 1 and not a.no_cpu:
             try:
-                r = time_cpu(n, 4, 1, pml=None, budget_s=15.0)
-                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"] = cpu_baseline(n, 2, 1, 3, budget_s=24.0)
             except Exception as e:  # the checker is optional for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "Gcell-updates/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         emit(line)
@@ -422,7 +556,19 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): n^3 per GPU; strong: n^3 in total, z-slabs of n/N planes (BASELINE configs[3])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (scaling probes)")
+    ap.add_argument("--reps", type=int, default=None, help="timed blocks of --steps steps (default 5); the median block is reported")
+    ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the 4-step parity spot check against the CPU checker (N = 1)")
+    ap.add_argument("--timeline", action="store_true", help="N > 1: record per-pass CUDA events on every rank -> gpurun_out/timeline_n<N>_rank<r>.json")
+    ap.add_argument("--cpu-leg", default=None, choices=["openmp", "kokkos"], help=argparse.SUPPRESS)
+    ap.add_argument("--nk", type=int, default=32, help=argparse.SUPPRESS)
     a = ap.parse_args()
+    a.reps_given = a.reps is not None
+    if a.reps is None:
+        a.reps = 5
+    a.reps = max(1, a.reps)
+    if a.cpu_leg:
+        cpu_leg_main(a)
+        return
     if a.warmup < 3:
         a.warmup = 3
     if a.impl == "reference":

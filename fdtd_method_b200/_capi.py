@@ -62,6 +62,8 @@ SIGNATURES = {
     "fdtd_read_slice": (_i, [_vp, _i, _i, _i, _vp, _sz, ctypes.POINTER(_sz)]),
     "fdtd_set_source": (_i, [_vp, _pi, _pi, _pd, _pd, _pd, _pd, _i]),
     "fdtd_clear_source": (_i, [_vp]),
+    "fdtd_issue": (_i, [_vp]),
+    "fdtd_flush": (_i, [_vp]),
     "fdtd_sync": (_i, [_vp]),
     "fdtd_device_ptr": (_i, [_vp, _i, ctypes.POINTER(_vp)]),
     "fdtd_get_info": (_i, [_vp, ctypes.POINTER(Info)]),

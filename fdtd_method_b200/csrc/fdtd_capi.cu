@@ -1373,6 +1373,19 @@ fdtd_status_t fdtd_clear_source(fdtd_solver_t* h) {
     return FDTD_OK;
 }
 
+fdtd_status_t fdtd_issue(fdtd_solver_t* h) {
+    Solver* s;
+    return enter(h, &s);
+}
+
+fdtd_status_t fdtd_flush(fdtd_solver_t* h) {
+    Solver* s;
+    fdtd_status_t st = enter(h, &s);
+    if (st != FDTD_OK) return st;
+    if ((st = flush_pending(s)) != FDTD_OK) return st;
+    return materialize_J(s);
+}
+
 fdtd_status_t fdtd_sync(fdtd_solver_t* h) {
     Solver* s;
     fdtd_status_t st = enter(h, &s);

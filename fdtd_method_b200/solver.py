@@ -100,6 +100,14 @@ class FDTD:
     def sync(self) -> None:
         _capi.check(_capi.lib().fdtd_sync(self._h))
 
+    def issue(self) -> None:
+        """Issue a recorded update_fields() call without waiting for the device."""
+        _capi.check(_capi.lib().fdtd_issue(self._h))
+
+    def flush(self) -> None:
+        """Issue deferred work (recorded step, trailing B half step) without waiting for the device."""
+        _capi.check(_capi.lib().fdtd_flush(self._h))
+
     def upload(self, comp, host: np.ndarray) -> None:
         a = np.ascontiguousarray(host, dtype=self.dtype)
         if a.size != self.local_cells:
@@ -183,6 +191,16 @@ class FDTD:
         ms = ctypes.c_double()
         _capi.check(_capi.lib().fdtd_timer_stop(self._h, ctypes.byref(ms)))
         return ms.value
+
+    def timeline_enable(self, max_passes: int) -> None:
+        _capi.check(_capi.lib().fdtd_timeline_enable(self._h, int(max_passes)))
+
+    def timeline_read(self, capacity: int = 4096) -> np.ndarray:
+        """[n_passes, 4] ms since the first pass start: pass start, halo copies start, halo copies done, pass end."""
+        out = np.zeros((capacity, 4), dtype=np.float64)
+        n = ctypes.c_int()
+        _capi.check(_capi.lib().fdtd_timeline_read(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), capacity, ctypes.byref(n)))
+        return out[:n.value].copy()
 
     def comm_init(self, unique_id: bytes) -> None:
         buf = ctypes.create_string_buffer(bytes(unique_id), _capi.NCCL_UNIQUE_ID_BYTES)

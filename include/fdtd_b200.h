@@ -182,6 +182,15 @@ fdtd_status_t fdtd_set_source(fdtd_solver_t* s, const int lo[3], const int hi[3]
                               const double* wy, const double* wz, const double* amp, int n_amp);
 fdtd_status_t fdtd_clear_source(fdtd_solver_t* s);
 
+/* Issue a recorded update_fields() call (see fdtd_update_fields) on the solver's stream; never waits for the device.
+ * A host thread that drives several slab solvers (fdtd_comm_init_local) calls this -- or fdtd_flush before B accesses --
+ * on ALL of them before any call that waits for one of them (uploads, downloads, scatter / gather, sync, destroy):
+ * a pass of one slab only completes once its neighbours have issued theirs. */
+fdtd_status_t fdtd_issue(fdtd_solver_t* s);
+/* Issue any deferred work (a recorded update_fields() call, the trailing B half step) on the solver's stream without
+ * waiting for it: afterwards the device arrays hold E(n), B(n) exactly as the reference's do when update_fields()
+ * returns.  (bench.py calls this before fdtd_timer_stop so that the closing half step is inside the timed region.) */
+fdtd_status_t fdtd_flush(fdtd_solver_t* s);
 /* Apply any deferred work and wait for the device (Kokkos::fence() in kokkos_sample.cpp:110-112). */
 fdtd_status_t fdtd_sync(fdtd_solver_t* s);
 

@@ -37,8 +37,23 @@ def main():
         ((64, 48, 24 * world), 0.1, True, np.float64, 6),      # PML two-step pass on slabs: T2 core + rim sweeps + mid-pass exchanges
         ((64, 40, 20 * world), 0.2, True, np.float64, 5),      # ... k shell takes a large part of the first / last slab
         ((64, 9, 16 * world), 0.07, True, np.float64, 5),      # ... no shell in j, thin shells elsewhere
+        # the benchmarked flavours on slab ranks: tiles wide enough for the TMA ring (Ni >= 122, Nj >= 26)
+        # reading ghost planes through the tensor maps (wrap_k = 0), both storage types, several k chunks per slab
+        # (chunk order 1..nz-1, 0 with the halo wait inside the kernel), and the PML two-step pass on top
+        ((128, 48, 12 * world), None, True, np.float64, 6),
+        ((192, 40, 40 * world), None, True, np.float64, 5),
+        ((128, 48, 64 * world), None, True, np.float64, 4),
+        ((136, 36, 24 * world), None, True, np.float32, 6),
+        ((128, 64, 40 * world), 0.1, True, np.float64, 6),
+        # uneven slabs around the two-step threshold: 5,4,.. planes -> every rank pairs; 4,..,3 -> nobody does
+        ((32, 16, 4 * world + 1), None, True, np.float64, 5),
+        ((32, 16, 4 * world - 1), None, True, np.float64, 5),
     ]
+    if os.environ.get("MGPU_CASES"):
+        sel = [int(v) for v in os.environ["MGPU_CASES"].split(",")]
+        cases = [cases[i] for i in sel]
     failures = 0
+    transport = in_kernel = None
     for shape, pml, fusion, dtype, steps in cases:
         Ni, Nj, Nk = shape
         d = (C, 1.25 * C, 0.8 * C)
@@ -50,12 +65,22 @@ def main():
         o = Oracle(Ni, Nj, Nk, d[0], d[1], d[2], 0.2, dtype=dtype, j_mode=J_KOKKOS, pml_percent=pml)
         f = seeded_fields(23, (Nk, Nj, Ni), dtype=dtype, same_j=False)
         kb, ke = g.k_begin, g.k_end
+        transport, in_kernel = g.info().transport, g.info().halo_in_kernel
         for c in range(9):
             o.field(c)[...] = f[c]
             g.upload(c, f[c][kb:ke])
         for t in range(steps):
             o.update_fields()
             g.update_fields()
+            if t == 0 and pml is None:
+                # collective slice read of a B component after an odd step: every rank flushes the deferred
+                # half step (ring exchange), the owner of the plane returns it
+                kq = Nk // 2
+                sl = g.read_slice(4, 2, kq)
+                own = kb <= kq < ke
+                if (sl is not None) != own or (own and not np.array_equal(sl, o.field(4)[kq])):
+                    failures += 1
+                    print(f"[rank {rank}] MISMATCH read_slice(By, k={kq}) {shape}", flush=True)
             if t == 1:   # mid-run read forces the deferred half step + ghost refresh path
                 for c in range(6):
                     if not np.array_equal(g.download(c), o.field(c)[kb:ke]):
@@ -73,7 +98,7 @@ def main():
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print(f"mgpu_worker: world={world} total mismatches={int(t[0])}", flush=True)
+        print(f"mgpu_worker: world={world} cases={len(cases)} transport={transport} halo_in_kernel={in_kernel} total mismatches={int(t[0])}", flush=True)
     dist.destroy_process_group()
     sys.exit(1 if int(t[0]) else 0)
 

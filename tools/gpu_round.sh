@@ -14,8 +14,11 @@
 #   e2e          tools/e2e_breakdown.py
 #   kc           DRAM traffic / duration of the T2 pass vs chunk length (512^3 and 1024^3)
 # N-GPU stages (set NGPU=2|4|8 and call gpurun --gpus $NGPU)
-#   mtests       tests/test_multi_gpu.py
-#   mbench       weak-scaling bench at $NGPU, PML bench at $NGPU, 1024^3 strong scaling at $NGPU, 1-GPU bench on the same box
+#   mtests       tests/test_multi_gpu.py (every transport; one-process ring)
+#   mcoarray     tests/test_cpp_api_gpu.py (coarray-style program with $NGPU images, C++ multi-GPU class)
+#   mbench       1-GPU bench on the same box, weak-scaling bench at $NGPU with the per-pass timeline, PML weak, 1024^3 strong
+#   mdriver      the driver's own command line at $NGPU
+#   mab          the other two halo transports at $NGPU, with timelines
 #   mprobe       tools/mgpu_probe.py (stream-structure variants)
 tag=${1:?tag}; shift
 out=gpurun_out/$tag; mkdir -p $out
@@ -42,8 +45,9 @@ tests)
   ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $out/pytest_gpu.log 2>&1; tail -3 $out/pytest_gpu.log
   timeout 300 python __graft_entry__.py --smoke > $out/smoke.log 2>&1; tail -2 $out/smoke.log ;;
 bench)
-  timeout 600 python bench.py --steps 200 --warmup 10 > $out/bench_n1.json 2> $out/bench_n1.err; cut -c1-300 $out/bench_n1.json
-  timeout 400 python bench.py --impl reference --steps 20 --warmup 3 > $out/bench_ref.json 2> $out/bench_ref.err; cut -c1-200 $out/bench_ref.json ;;
+  timeout 600 python bench.py --steps 20 --warmup 5 > $out/bench_n1_driver_args.json 2> $out/bench_n1_driver_args.err; cut -c1-400 $out/bench_n1_driver_args.json
+  timeout 600 python bench.py --steps 200 --warmup 10 --no-cpu > $out/bench_n1.json 2> $out/bench_n1.err; cut -c1-300 $out/bench_n1.json
+  timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > $out/bench_ref.json 2> $out/bench_ref.err; cut -c1-200 $out/bench_ref.json ;;
 table)
   timeout 900 python tools/config_table.py > $out/config_table.jsonl 2> $out/config_table.err; cut -c1-220 $out/config_table.jsonl ;;
 launches)
@@ -70,12 +74,22 @@ kc)
     ncu_rows $out/kc_${n}_$kc.csv n=$n kc=$kc
   done | tee $out/kc_traffic.jsonl ;;
 mtests)
-  ( time timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > $out/pytest_mgpu.log 2>&1; tail -4 $out/pytest_mgpu.log | cut -c1-300 ;;
-mbench)
-  timeout 600 $TR --master-port 29521 bench.py --gpus $N --steps 200 --warmup 10 > $out/bench_n$N.json 2> $out/bench_n$N.err; cut -c1-300 $out/bench_n$N.json
-  timeout 600 $TR --master-port 29522 bench.py --gpus $N --steps 100 --warmup 10 --workload pml --no-e2e > $out/bench_pml_n$N.json 2> $out/bench_pml_n$N.err; cut -c1-300 $out/bench_pml_n$N.json
-  timeout 600 $TR --master-port 29523 bench.py --gpus $N --steps 100 --warmup 10 --size 1024 --scaling strong --no-e2e > $out/bench_strong1024_n$N.json 2> $out/bench_strong1024_n$N.err; cut -c1-300 $out/bench_strong1024_n$N.json
-  timeout 600 python bench.py --steps 200 --warmup 10 --no-cpu --no-e2e > $out/bench_n1_samebox.json 2> $out/bench_n1_samebox.err; cut -c1-300 $out/bench_n1_samebox.json ;;
+  ( time timeout 1500 python -m pytest tests/test_multi_gpu.py -m gpu -q -rs ) > $out/pytest_mgpu_n$N.log 2>&1; tail -6 $out/pytest_mgpu_n$N.log | cut -c1-300 ;;
+mcoarray)   # the coarray-style program with $N images (cpp/coarray, f4) + the C++ multi-GPU class tests
+  ( timeout 600 python -m pytest tests/test_cpp_api_gpu.py -m gpu -q -rs ) > $out/pytest_cpp_n$N.log 2>&1; tail -4 $out/pytest_cpp_n$N.log | cut -c1-300 ;;
+mbench)     # weak scaling (the driver's contract) with the per-pass timeline, same-box N = 1, PML weak, 1024^3 strong
+  timeout 600 python bench.py --steps 200 --warmup 10 --reps 3 --no-cpu --no-e2e --no-verify > $out/bench_n1_samebox.json 2> $out/bench_n1_samebox.err; cut -c1-300 $out/bench_n1_samebox.json
+  timeout 600 $TR --master-port 29521 bench.py --gpus $N --steps 200 --warmup 10 --reps 3 --no-e2e --timeline > $out/bench_n$N.json 2> $out/bench_n$N.err; cut -c1-300 $out/bench_n$N.json
+  mkdir -p $out/timeline_n$N; mv gpurun_out/timeline_n${N}_rank*.json $out/timeline_n$N/ 2>/dev/null
+  timeout 600 $TR --master-port 29522 bench.py --gpus $N --steps 100 --warmup 10 --reps 3 --workload pml --no-e2e > $out/bench_pml_n$N.json 2> $out/bench_pml_n$N.err; cut -c1-300 $out/bench_pml_n$N.json
+  timeout 600 $TR --master-port 29523 bench.py --gpus $N --steps 100 --warmup 10 --reps 3 --size 1024 --scaling strong --no-e2e > $out/bench_strong1024_n$N.json 2> $out/bench_strong1024_n$N.err; cut -c1-300 $out/bench_strong1024_n$N.json ;;
+mdriver)    # exactly what the driver runs at N > 1 (short window, e2e leg included)
+  timeout 600 $TR --master-port 29531 bench.py --gpus $N --steps 20 --warmup 5 > $out/bench_n${N}_driver_args.json 2> $out/bench_n${N}_driver_args.err; cut -c1-300 $out/bench_n${N}_driver_args.json ;;
+mab)        # transports side by side: copy engines + halo wait in the kernel (default) / + three-stream boundary launches / NCCL
+  FDTD_B200_HALO_IN_KERNEL=0 timeout 600 $TR --master-port 29524 bench.py --gpus $N --steps 200 --warmup 10 --reps 3 --no-e2e --timeline > $out/bench_n${N}_peer3stream.json 2> $out/bench_n${N}_peer3stream.err; cut -c1-300 $out/bench_n${N}_peer3stream.json
+  mkdir -p $out/timeline_n${N}_peer3stream; mv gpurun_out/timeline_n${N}_rank*.json $out/timeline_n${N}_peer3stream/ 2>/dev/null
+  FDTD_B200_TRANSPORT=nccl timeout 600 $TR --master-port 29525 bench.py --gpus $N --steps 200 --warmup 10 --reps 3 --no-e2e --timeline > $out/bench_n${N}_nccl.json 2> $out/bench_n${N}_nccl.err; cut -c1-300 $out/bench_n${N}_nccl.json
+  mkdir -p $out/timeline_n${N}_nccl; mv gpurun_out/timeline_n${N}_rank*.json $out/timeline_n${N}_nccl/ 2>/dev/null ;;
 mprobe)
   timeout 600 $TR --master-port 29511 tools/mgpu_probe.py > $out/mgpu_probe.log 2>&1; grep variant $out/mgpu_probe.log ;;
 *) echo "unknown stage $stage" ;;
