@@ -18,6 +18,7 @@ PML_NONE, PML_PERCENT, PML_THICKNESS = 0, 1, 2
 FLAG_J_OPENMP_QUIRK, FLAG_NO_FUSION, FLAG_NO_GRAPH, FLAG_NO_OVERLAP = 0x1, 0x2, 0x4, 0x8
 FLAG_NO_PML_SPLIT = 0x10
 FLAG_NO_TEMPORAL = 0x20
+FLAG_UNIFORM_SLABS = 0x40
 NCCL_UNIQUE_ID_BYTES = 128
 
 OK, ERR_INVALID_PARAMETERS, ERR_INVALID_COMPONENT, ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_NOMEM, ERR_BAD_ARGUMENT = range(8)
@@ -76,6 +77,7 @@ SIGNATURES = {
     "fdtd_timeline_enable": (_i, [_vp, _i]),
     "fdtd_timeline_read": (_i, [_vp, _pd, _i, _pi]),
     "fdtd_slab_range": (None, [_i, _i, _i, _pi, _pi]),
+    "fdtd_slab_range_cfg": (None, [ctypes.POINTER(Config), _i, _pi, _pi]),
     "fdtd_pml_profile": (_i, [_i, _i, _d, _d, _pd, _pd, _pd]),
     "fdtd_pml_thickness": (_i, [_i, _d]),
     "fdtd_last_error": (ctypes.c_char_p, []),

@@ -910,7 +910,14 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
     s->esz = (cfg->dtype == FDTD_F32) ? 4 : 8;
 
     int k_begin, k_end;
-    fdtd_slab_range(P.Nk, cfg->rank, cfg->nranks, &k_begin, &k_end);
+    fdtd_slab_range_cfg(cfg, cfg->rank, &k_begin, &k_end);
+    int min_slab = P.Nk;   // the smallest slab of the ring: decides, identically on every rank, which passes are used
+    for (int r = 0; r < cfg->nranks; ++r) {
+        int b, e;
+        fdtd_slab_range_cfg(cfg, r, &b, &e);
+        min_slab = std::min(min_slab, e - b);
+    }
+    if (min_slab < 1) { delete s; return fail(FDTD_ERR_BAD_ARGUMENT, "more ranks than k planes"); }
     s->g.Ni = P.Ni; s->g.Nj = P.Nj; s->g.Nk = P.Nk;
     s->g.nk = k_end - k_begin;
     s->g.k0 = k_begin;
@@ -963,11 +970,11 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
     s->fused = !s->has_pml && !(cfg->flags & FDTD_FLAG_NO_FUSION) && (P.Ni % V == 0);
     // (decided from the smallest slab of the ring, not the local one: every rank must take the same path, or the
     // exchange plans of neighbours do not match -- fdtd_slab_range gives the remainder planes to the low ranks)
-    s->t2 = s->fused && !(cfg->flags & FDTD_FLAG_NO_TEMPORAL) && P.Nk / cfg->nranks >= 4;
+    s->t2 = s->fused && !(cfg->flags & FDTD_FLAG_NO_TEMPORAL) && min_slab >= 4;
     // fp64 by default: the fp32 T2 pass is conversion-bound and loses to the two lean interior sweeps
     // (measured 5.5 vs 4.8 ms per step at 512^3); FDTD_B200_PML_T2_F32=1 turns it on anyway (parity tests do).
     const bool pair_dtype_ok = (s->esz == 8) || s->tun.pml_t2_f32;
-    if (s->has_pml && pair_dtype_ok && !(cfg->flags & (FDTD_FLAG_NO_FUSION | FDTD_FLAG_NO_TEMPORAL)) && (P.Ni % V == 0) && P.Nk / cfg->nranks >= 4) {
+    if (s->has_pml && pair_dtype_ok && !(cfg->flags & (FDTD_FLAG_NO_FUSION | FDTD_FLAG_NO_TEMPORAL)) && (P.Ni % V == 0) && min_slab >= 4) {
         // store box of the two-step pass: main box shrunk by the pass's reach on the axes that have a shell
         bool ok = true;
         for (int a = 0; a < 3; ++a) {
@@ -1147,6 +1154,46 @@ void fdtd_slab_range(int Nk, int rank, int nranks, int* k_begin, int* k_end) {
     const int b = rank * base + (rank < rem ? rank : rem);
     if (k_begin) *k_begin = b;
     if (k_end) *k_end = b + base + (rank < rem ? 1 : 0);
+}
+
+// Cost-weighted z slabs for PML solvers (SURVEY.md 8(e) "PML interaction").  A shell cell moves 36 words per step through
+// the rim sweeps, a core cell 6 through the two-step pass (measured 512^3 / 32: 120 vs 21 ps per cell-pair,
+// profiles/ncu_pml_r01.md), so a plane inside the k shell costs Ni*Nj*W and a plane of the main k range
+// shell_ij*W + core_ij with W = 6; without a k shell (or one rank, or FDTD_FLAG_UNIFORM_SLABS) the split is the uniform one.
+// Boundaries are the points where the running cost crosses r/nranks of the total (every rank keeps >= 1 plane).
+void fdtd_slab_range_cfg(const fdtd_config_t* cfg, int rank, int* k_begin, int* k_end) {
+    const fdtd_params_t& P = cfg->grid;
+    const int n = cfg->nranks < 1 ? 1 : cfg->nranks;
+    int pml[3] = {0, 0, 0};
+    if (cfg->pml_mode == FDTD_PML_PERCENT) {
+        pml[0] = fdtd_pml_thickness(P.Ni, cfg->pml_percent); pml[1] = fdtd_pml_thickness(P.Nj, cfg->pml_percent); pml[2] = fdtd_pml_thickness(P.Nk, cfg->pml_percent);
+    } else if (cfg->pml_mode == FDTD_PML_THICKNESS) {
+        for (int a = 0; a < 3; ++a) pml[a] = cfg->pml_thickness[a];
+    }
+    const bool weighted = n > 1 && pml[2] > 0 && 2 * pml[2] <= P.Nk && 2 * pml[0] <= P.Ni && 2 * pml[1] <= P.Nj &&
+                          !(cfg->flags & FDTD_FLAG_UNIFORM_SLABS) && P.Nk >= 8 * n;
+    if (!weighted) { fdtd_slab_range(P.Nk, rank, n, k_begin, k_end); return; }
+    const double W = 6.0;
+    const double core_ij = (double)(P.Ni - 2 * pml[0]) * (double)(P.Nj - 2 * pml[1]);
+    const double shell_plane = (double)P.Ni * P.Nj * W, main_plane = ((double)P.Ni * P.Nj - core_ij) * W + core_ij;
+    const double total = 2.0 * pml[2] * shell_plane + (double)(P.Nk - 2 * pml[2]) * main_plane;
+    auto boundary = [&](int r) -> int {   // first plane of rank r
+        if (r <= 0) return 0;
+        if (r >= n) return P.Nk;
+        const double target = total * r / n;
+        double acc = 0.0;
+        int k = 0;
+        for (; k < P.Nk; ++k) {
+            const double c = (k < pml[2] || k >= P.Nk - pml[2]) ? shell_plane : main_plane;
+            if (acc + 0.5 * c >= target) break;
+            acc += c;
+        }
+        // keep at least 4 planes per rank (the two-step pass), whatever the weights say
+        const int lo = 4 * r, hi = P.Nk - 4 * (n - r);
+        return k < lo ? lo : (k > hi ? hi : k);
+    };
+    if (k_begin) *k_begin = boundary(rank);
+    if (k_end) *k_end = boundary(rank + 1);
 }
 
 void fdtd_config_init(fdtd_config_t* cfg) {

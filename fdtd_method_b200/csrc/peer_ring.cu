@@ -74,7 +74,7 @@ static void neighbours(const Solver* s, PeerRing* r) {
     r->up = (me + 1) % P;
     r->down = (me + P - 1) % P;
     int b, e;
-    fdtd_slab_range(s->g.Nk, r->down, P, &b, &e);
+    fdtd_slab_range_cfg(&s->cfg, r->down, &b, &e);
     r->nk_down = e - b;
 }
 

@@ -76,6 +76,7 @@ typedef enum fdtd_status {
 #define FDTD_FLAG_NO_OVERLAP 0x8u     /* multi-GPU: issue the halo exchange on the compute stream (no overlap) */
 #define FDTD_FLAG_NO_PML_SPLIT 0x10u  /* PML: one launch per sweep with a per-cell predicate instead of interior + shell launches */
 #define FDTD_FLAG_NO_TEMPORAL 0x20u   /* fdtd_step(n): never pair steps into the temporally blocked two-step pass */
+#define FDTD_FLAG_UNIFORM_SLABS 0x40u /* multi-GPU PML: equal slab heights instead of cost-weighted ones (fdtd_slab_range_cfg) */
 
 typedef enum fdtd_pml_mode {
     FDTD_PML_NONE = 0,     /* class FDTD: periodic everywhere */
@@ -242,6 +243,11 @@ fdtd_status_t fdtd_timeline_enable(fdtd_solver_t* s, int max_passes);
 fdtd_status_t fdtd_timeline_read(fdtd_solver_t* s, double* ms, int capacity_passes, int* n_passes);
 /* Plane range owned by `rank` of `nranks` for a grid with Nk planes (remainder spread over low ranks). */
 void fdtd_slab_range(int Nk, int rank, int nranks, int* k_begin, int* k_end);
+
+/* Plane range of `rank` for the solver described by cfg (cfg->nranks ranks).  Equal to fdtd_slab_range() unless the
+ * solver has a PML shell in k: then slab heights are cost-weighted (a shell cell moves 36 words per step, a core cell 6),
+ * so the ranks that own k-shell planes get fewer planes.  fdtd_get_info() reports the range in use. */
+void fdtd_slab_range_cfg(const fdtd_config_t* cfg, int rank, int* k_begin, int* k_end);
 
 /* ---- host-only helpers (no GPU needed) ---------------------------------- */
 /* 1-D PML tables for one axis, from src/FDTD/FDTD_PML.cpp:3-65,98-111,316-338:

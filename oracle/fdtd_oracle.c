@@ -89,6 +89,16 @@ DECL_TYPED(oracle_f32_t, float)
 #undef SUFFIX
 #undef oracle_t
 
+/* float storage AND float arithmetic (the GPU library's opt-in FDTD_FLAG_F32_ARITH mode; is_f32 == 2) */
+#define REAL float
+#define ARITH float
+#define SUFFIX _f32a
+#define oracle_t oracle_f32_t
+#include "fdtd_oracle_body.inc"
+#undef REAL
+#undef SUFFIX
+#undef oracle_t
+
 typedef oracle_t_untyped oracle_t;
 
 /* PML profile for one axis.  Follows src/FDTD/FDTD_PML.cpp:254-256 (thickness),
@@ -173,13 +183,13 @@ double oracle_coef(oracle_t *o, int which) {   /* 0-2 cE, 3-5 cB, 6 cJ */
 }
 
 void oracle_update_B(oracle_t *o) {
-    if (o->is_f32) update_B_f32((oracle_f32_t *)o); else update_B_f64((oracle_f64_t *)o);
+    if (o->is_f32 == 2) update_B_f32a((oracle_f32_t *)o); else if (o->is_f32) update_B_f32((oracle_f32_t *)o); else update_B_f64((oracle_f64_t *)o);
 }
 void oracle_update_E(oracle_t *o) {
-    if (o->is_f32) update_E_f32((oracle_f32_t *)o); else update_E_f64((oracle_f64_t *)o);
+    if (o->is_f32 == 2) update_E_f32a((oracle_f32_t *)o); else if (o->is_f32) update_E_f32((oracle_f32_t *)o); else update_E_f64((oracle_f64_t *)o);
 }
 void oracle_update_fields(oracle_t *o) {
-    if (o->is_f32) update_fields_f32((oracle_f32_t *)o); else update_fields_f64((oracle_f64_t *)o);
+    if (o->is_f32 == 2) update_fields_f32a((oracle_f32_t *)o); else if (o->is_f32) update_fields_f32((oracle_f32_t *)o); else update_fields_f64((oracle_f64_t *)o);
 }
 void oracle_step(oracle_t *o, int nsteps) {
     for (int s = 0; s < nsteps; s++) oracle_update_fields(o);

@@ -86,12 +86,16 @@ class Oracle:
             cls._lib = L
         return cls._lib
 
-    def __init__(self, Ni, Nj, Nk, dx, dy, dz, dt, dtype=np.float64, j_mode=J_KOKKOS, pml_percent=None):
+    def __init__(self, Ni, Nj, Nk, dx, dy, dz, dt, dtype=np.float64, j_mode=J_KOKKOS, pml_percent=None, f32_arith=False):
+        """f32_arith (float32 only): evaluate the updates in float instead of double -- the restatement of the GPU
+        library's opt-in FDTD_FLAG_F32_ARITH mode, not of anything the reference builds."""
         L = self.lib()
         self.shape = (Nk, Nj, Ni)  # numpy view: k slowest, i fastest (index i + j*Ni + k*Ni*Nj)
         self.dtype = np.dtype(dtype)
         self.has_pml = pml_percent is not None
-        self._h = L.oracle_create(Ni, Nj, Nk, dx, dy, dz, dt, int(self.dtype == np.float32), j_mode,
+        if f32_arith and self.dtype != np.float32:
+            raise TypeError("f32_arith needs dtype=float32")
+        self._h = L.oracle_create(Ni, Nj, Nk, dx, dy, dz, dt, (2 if f32_arith else 1) if self.dtype == np.float32 else 0, j_mode,
                                   -1.0 if pml_percent is None else float(pml_percent))
         if not self._h:
             raise ValueError("ERROR: invalid parameters")

@@ -86,3 +86,43 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "fdtd_oracle" not in txt, f
+
+
+def test_cost_weighted_slabs_for_pml():
+    """fdtd_slab_range_cfg: uniform unless the solver has a PML shell in k; then the ranks that own k-shell planes get
+    fewer planes (36 vs 6 words per cell-step), the ranges still tile the grid and every rank keeps >= 4 planes."""
+    import ctypes
+    L = _capi.lib()
+
+    def ranges(Ni, Nj, Nk, n, mode, thick=(0, 0, 0), pct=0.0, flags=0):
+        cfg = _capi.Config()
+        L.fdtd_config_init(ctypes.byref(cfg))
+        cfg.grid = fb.Parameters(Ni, Nj, Nk, 0, 1, 0, 1, 0, 1, 1, 1, 1)
+        cfg.dt, cfg.nranks, cfg.pml_mode, cfg.pml_percent, cfg.flags = 0.2, n, mode, pct, flags
+        for a in range(3):
+            cfg.pml_thickness[a] = thick[a]
+        out = []
+        for r in range(n):
+            b, e = ctypes.c_int(), ctypes.c_int()
+            L.fdtd_slab_range_cfg(ctypes.byref(cfg), r, ctypes.byref(b), ctypes.byref(e))
+            out.append((b.value, e.value))
+        return out
+
+    for n in (1, 2, 3, 4, 8):
+        Nk = 512 * n
+        assert ranges(512, 512, Nk, n, _capi.PML_NONE) == [fb.slab_range(Nk, r, n) for r in range(n)]
+        assert ranges(512, 512, Nk, n, _capi.PML_THICKNESS, (32, 32, 32), flags=_capi.FLAG_UNIFORM_SLABS) == [fb.slab_range(Nk, r, n) for r in range(n)]
+        w = ranges(512, 512, Nk, n, _capi.PML_THICKNESS, (32, 32, 32))
+        assert w[0][0] == 0 and w[-1][1] == Nk and all(a[1] == b[0] for a, b in zip(w, w[1:]))
+        assert all(e - b >= 4 for b, e in w)
+        if n >= 3:
+            h = [e - b for b, e in w]
+            assert h[0] < h[1] and h[-1] < h[-2] and h[0] == h[-1]        # the k-shell owners are shorter
+            # cost balance within 1.5 % (shell cell 6, core cell 1)
+            core = 448 * 448
+            main, shell = (512 * 512 - core) * 6 + core, 512 * 512 * 6
+            cost = [sum(shell if (k < 32 or k >= Nk - 32) else main for k in range(b, e)) for b, e in w]
+            assert max(cost) / min(cost) < 1.015, cost
+    # no shell in k -> uniform; tiny grids -> uniform
+    assert ranges(64, 64, 64, 4, _capi.PML_THICKNESS, (8, 8, 0)) == [fb.slab_range(64, r, 4) for r in range(4)]
+    assert ranges(16, 16, 16, 4, _capi.PML_PERCENT, pct=0.2) == [fb.slab_range(16, r, 4) for r in range(4)]

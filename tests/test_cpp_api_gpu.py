@@ -82,7 +82,38 @@ def test_sample_clone_writes_the_visualisation_csvs(cpp_bins, golden_dir, tmp_pa
     assert _slice_rows(r.stdout) == got
 
 
-@pytest.mark.parametrize("images", [1, 2])
+def test_kokkos_sample_clone(cpp_bins, golden_dir):
+    """./kokkos_sample_b200: handles held across steps, operator(), per-step re-zero after the source window
+    (kokkos_sample.cpp:82-84,105-107,114-129) -- prints the YZ slice of the real reference."""
+    r = subprocess.run([os.path.join(cpp_bins, "kokkos_sample_b200")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.startswith("Execution time: ")
+    yz = json.load(open(os.path.join(golden_dir, "sample_32_100_periodic.json")))["slice_EX_yz"]
+    assert _slice_rows(r.stdout) == [[f"{v:.5f}" for v in row] for row in yz]
+    assert _slice_rows(r.stdout)[0][:3] == ["0.04722", "0.00665", "-0.01068"]
+
+
+@pytest.mark.parametrize("ngpu", [2, 4])
+@pytest.mark.parametrize("prog", ["sample_b200", "kokkos_sample_b200"])
+def test_drop_in_class_on_several_gpus(cpp_bins, golden_dir, gpu_count, ngpu, prog):
+    """FDTD_b200::FDTD / FDTD_PML spanning several GPUs in ONE process (FDTD_B200_GPUS): the unmodified caller programs
+    print the real reference's slices -- z slabs, copy-engine halo ring, get_field gathering the slabs."""
+    if gpu_count < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    args = ["pml"] if prog == "sample_b200" else []
+    r = subprocess.run([os.path.join(cpp_bins, prog), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300,
+                       env=dict(os.environ, FDTD_B200_GPUS=str(ngpu)))
+    assert r.returncode == 0, r.stdout
+    gold = json.load(open(os.path.join(golden_dir, "sample_32_100_periodic.json")))
+    if prog == "sample_b200":
+        pml = json.load(open(os.path.join(golden_dir, "sample_32_100_pml02.json")))["slice_EX_xy"]
+        assert _slice_rows(r.stdout) == [[f"{v:.5f}" for v in row] for row in gold["slice_EX_xy"]]
+        assert _slice_rows(r.stdout, after="PML:") == [[f"{v:.5f}" for v in row] for row in pml]
+    else:
+        assert _slice_rows(r.stdout) == [[f"{v:.5f}" for v in row] for row in gold["slice_EX_yz"]]
+
+
+@pytest.mark.parametrize("images", [1, 2, 4])
 def test_coarray_program(cpp_bins, golden_dir, gpu_count, images):
     """coarray/fdtd.F90's program (one image per GPU): banner lines and the 10x10 Ex slice, which for
     the 32^3 x 100 scenario is the slice the real reference's sample prints (same source, same steps)."""
