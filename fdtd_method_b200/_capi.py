@@ -19,6 +19,7 @@ FLAG_J_OPENMP_QUIRK, FLAG_NO_FUSION, FLAG_NO_GRAPH, FLAG_NO_OVERLAP = 0x1, 0x2, 
 FLAG_NO_PML_SPLIT = 0x10
 FLAG_NO_TEMPORAL = 0x20
 FLAG_UNIFORM_SLABS = 0x40
+FLAG_F32_ARITH = 0x80
 NCCL_UNIQUE_ID_BYTES = 128
 
 OK, ERR_INVALID_PARAMETERS, ERR_INVALID_COMPONENT, ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_NOMEM, ERR_BAD_ARGUMENT = range(8)
@@ -40,7 +41,8 @@ class Info(ctypes.Structure):
                 ("launches", ctypes.c_int64), ("steps_done", ctypes.c_int64),
                 ("fused", ctypes.c_int32), ("rank", ctypes.c_int32), ("nranks", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("temporal", ctypes.c_int32), ("passes_t2", ctypes.c_int64),
-                ("kernel_ns", ctypes.c_int64), ("transport", ctypes.c_int32), ("halo_in_kernel", ctypes.c_int32)]
+                ("kernel_ns", ctypes.c_int64), ("transport", ctypes.c_int32), ("halo_in_kernel", ctypes.c_int32),
+                ("f32_arith", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
 
 
 # every entry point include/fdtd_b200.h declares: name -> (restype, argtypes)

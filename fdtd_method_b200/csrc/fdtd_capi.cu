@@ -93,7 +93,7 @@ static int pick_kc(const Solver* s, int tiles_ij, int nplanes) {
     return kc;
 }
 
-template <typename T>
+template <typename T, typename A = double>
 static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) {
     constexpr int V = VecOf<T>::V;
     SweepArgs<T> a;
@@ -110,8 +110,8 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
     const int gz = (s->g.nk + a.kc - 1) / a.kc;
     dim3 grid(gx, gy, gz);
     if (!s->has_pml) {
-        if (is_B) sweep_B_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
-        else sweep_E_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
+        if (is_B) sweep_B_kernel<T, false, V, A><<<grid, block, 0, s->stream>>>(a);
+        else sweep_E_kernel<T, false, V, A><<<grid, block, 0, s->stream>>>(a);
         FDTD_CUDA_TRY(cudaGetLastError());
         s->launches++;
         return FDTD_OK;
@@ -127,8 +127,8 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
                        inner >= (1 << 15) && !(s->cfg.flags & FDTD_FLAG_NO_PML_SPLIT);
     if (split) {
         a.mode = 1;
-        if (is_B) sweep_B_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
-        else sweep_E_kernel<T, false><<<grid, block, 0, s->stream>>>(a);
+        if (is_B) sweep_B_kernel<T, false, V, A><<<grid, block, 0, s->stream>>>(a);
+        else sweep_E_kernel<T, false, V, A><<<grid, block, 0, s->stream>>>(a);
         FDTD_CUDA_TRY(cudaGetLastError());
         s->launches++;
         a.mode = 2;
@@ -138,8 +138,8 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
     // the PML = true instantiation: 2 cells per thread for float storage (see sweep_kernels.cuh)
     constexpr int VP = (sizeof(T) == 4) ? 2 : V;
     const dim3 grid_p((s->g.Ni + SWEEP_BX * VP - 1) / (SWEEP_BX * VP), gy, gz);
-    if (is_B) sweep_B_kernel<T, true, VP><<<grid_p, block, 0, s->stream>>>(a);
-    else sweep_E_kernel<T, true, VP><<<grid_p, block, 0, s->stream>>>(a);
+    if (is_B) sweep_B_kernel<T, true, VP, A><<<grid_p, block, 0, s->stream>>>(a);
+    else sweep_E_kernel<T, true, VP, A><<<grid_p, block, 0, s->stream>>>(a);
     FDTD_CUDA_TRY(cudaGetLastError());
     s->launches++;
     return FDTD_OK;
@@ -148,7 +148,7 @@ static fdtd_status_t launch_sweep(Solver* s, bool is_B, int n_half, int do_pml) 
 // Rim sweep of the PML solver's two-step pass: the PML = true kernel over every cell OUTSIDE the box ib (vector
 // granularity in i), reading generation `cur`; `to_new` = write the other generation instead of updating in place
 // (B sweep: B' -> gen cur^1; E sweep: reads B from gen cur^1, old E from gen cur, E' -> gen cur^1).
-template <typename T>
+template <typename T, typename A = double>
 static fdtd_status_t launch_rim_sweep(Solver* s, bool is_B, int n_half, const int ib_lo[3], const int ib_hi[3], bool to_new) {
     constexpr int V = VecOf<T>::V;
     SweepArgs<T> a;
@@ -175,8 +175,8 @@ static fdtd_status_t launch_rim_sweep(Solver* s, bool is_B, int n_half, const in
     const int gy = (s->g.Nj + SWEEP_BY - 1) / SWEEP_BY;
     a.kc = pick_kc(s, gx * gy, s->g.nk);
     dim3 grid(gx, gy, (s->g.nk + a.kc - 1) / a.kc);
-    if (is_B) sweep_B_kernel<T, true, VP><<<grid, block, 0, s->stream>>>(a);
-    else sweep_E_kernel<T, true, VP><<<grid, block, 0, s->stream>>>(a);
+    if (is_B) sweep_B_kernel<T, true, VP, A><<<grid, block, 0, s->stream>>>(a);
+    else sweep_E_kernel<T, true, VP, A><<<grid, block, 0, s->stream>>>(a);
     FDTD_CUDA_TRY(cudaGetLastError());
     s->launches++;
     return FDTD_OK;
@@ -282,15 +282,15 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
 
 // ---- temporally blocked pass: two Yee steps per launch (fused_kernel_t2.cuh) -------------------------------
 // Variant table <BY rows per CTA, min CTAs/SM>; FDTD_B200_T2_VARIANT picks one.
-template <typename T, int BY, int MINB, int ABL = 0>
+template <typename T, typename A, int BY, int MINB, int ABL = 0>
 static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, int cfg_bit) {
-    constexpr int V = T2_V;   // 2 cells per lane for both storage types
+    constexpr int V = t2_v<A>();   // cells per lane: 2 with double arithmetic (both storage types), 4 with float arithmetic
     constexpr int TIU = FUSED_OUT_LANES * V;
     constexpr int TJU = BY - 4;
-    constexpr size_t smem = fused_t2_smem_bytes<T, BY>();
+    constexpr size_t smem = fused_t2_smem_bytes<T, A, BY>();
     if (!(s->configured & (1u << cfg_bit))) {
-        cudaError_t e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, MINB, true, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, BY, MINB, false, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, A, BY, MINB, true, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_BE_T2_kernel<T, A, BY, MINB, false, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         s->configured |= (1u << cfg_bit);
     }
@@ -338,8 +338,8 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, int cfg_bit) 
     // Halo-dependent chunks last: with the chunk order 1, 2, ..., nz-1, 0 the CTAs that read ghost planes (top chunk at
     // its end, bottom chunk at its start) are dispatched after the interior ones, when the pushed planes have long landed.
     a.z_rot = (a.halo_flags != nullptr && np2 == 0 && a.nz1 > 1) ? 1 : 0;
-    if (a.n_half == 2) fused_BE_T2_kernel<T, BY, MINB, true, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
-    else fused_BE_T2_kernel<T, BY, MINB, false, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
+    if (a.n_half == 2) fused_BE_T2_kernel<T, A, BY, MINB, true, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
+    else fused_BE_T2_kernel<T, A, BY, MINB, false, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -361,7 +361,8 @@ static tmap_encode_fn tmap_encoder() {
 static bool encode_tmap(const Solver* s, tmap_encode_fn enc, CUtensorMap* tm, int comp, int gen, int by) {
     const cuuint64_t dims[3] = {(cuuint64_t)s->g.Ni, (cuuint64_t)s->g.Nj, (cuuint64_t)(s->g.nk + 2 * GHOST_PLANES)};
     const cuuint64_t strides[2] = {(cuuint64_t)s->g.pitch * s->esz, (cuuint64_t)s->g.plane * s->esz};
-    const cuuint32_t box[3] = {(cuuint32_t)(s->esz == 8 ? t2_rbox<double>() : t2_rbox<float>()), (cuuint32_t)by, 1u};   // 64 cells = 512 B (fp64) / 68 cells = 272 B (fp32)
+    // 64 cells = 512 B (fp64) / 68 cells = 272 B (fp32 storage, double arithmetic) / 128 cells = 512 B (fp32 storage and arithmetic)
+    const cuuint32_t box[3] = {(cuuint32_t)(s->esz == 8 ? t2_rbox<double, double>() : s->f32_arith ? t2_rbox<float, float>() : t2_rbox<float, double>()), (cuuint32_t)by, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (box[0] > (cuuint32_t)s->g.Ni || by > s->g.Nj) return false;   // no wrap-free tile exists anyway
     const int promo = s->tun.tma_l2;   // FDTD_B200_TMA_L2 = 0 none, 64, 128, 256 (default; measured, profiles/tma_l2_r01.jsonl)
@@ -387,7 +388,7 @@ static const CUtensorMap* cached_tmaps(Solver* s, int gen, int by) {
     return s->tmaps[gen];
 }
 
-template <typename T>
+template <typename T, typename A = double>
 static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_lo2, int k_hi2, int src2, double amp2, unsigned halo_seq) {
     static const int by_of_variant[] = {16, 8, 12};
     int variant = s->tun.t2_variant;
@@ -424,14 +425,14 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
     cudaError_t e;
     switch (variant) {
         default:
-        case 0: e = launch_t2_variant<T, 16, 1>(s, a, CFG_T2 + 0); break;
-        case 1: e = launch_t2_variant<T, 8, 2>(s, a, CFG_T2 + 1); break;
-        case 2: e = launch_t2_variant<T, 12, 1>(s, a, CFG_T2 + 2); break;
+        case 0: e = launch_t2_variant<T, A, 16, 1>(s, a, CFG_T2 + 0 + (sizeof(A) == 4 ? 8 : 0)); break;
+        case 1: e = launch_t2_variant<T, A, 8, 2>(s, a, CFG_T2 + 1 + (sizeof(A) == 4 ? 8 : 0)); break;
+        case 2: e = launch_t2_variant<T, A, 12, 1>(s, a, CFG_T2 + 2 + (sizeof(A) == 4 ? 8 : 0)); break;
 #ifdef FDTD_T2_ABLATE   /* timing experiments only: results are wrong */
-        case 11: e = launch_t2_variant<T, 16, 1, 1>(s, a, CFG_T2 + 3); break;
-        case 12: e = launch_t2_variant<T, 16, 1, 2>(s, a, CFG_T2 + 4); break;
-        case 13: e = launch_t2_variant<T, 16, 1, 3>(s, a, CFG_T2 + 5); break;
-        case 14: e = launch_t2_variant<T, 16, 1, 4>(s, a, CFG_T2 + 6); break;
+        case 11: e = launch_t2_variant<T, A, 16, 1, 1>(s, a, CFG_T2 + 3); break;
+        case 12: e = launch_t2_variant<T, A, 16, 1, 2>(s, a, CFG_T2 + 4); break;
+        case 13: e = launch_t2_variant<T, A, 16, 1, 3>(s, a, CFG_T2 + 5); break;
+        case 14: e = launch_t2_variant<T, A, 16, 1, 4>(s, a, CFG_T2 + 6); break;
 #endif
     }
     if (e != cudaSuccess) return cuda_fail(e, "fused_BE_T2_kernel launch");
@@ -457,6 +458,8 @@ static fdtd_status_t launch_source(Solver* s, double amp, int zero) {
 }
 
 #define DISPATCH(s, fn, ...) ((s)->dtype == FDTD_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+// (storage, arithmetic) pairs: (double, double), (float, double) and, with FDTD_FLAG_F32_ARITH, (float, float)
+#define DISPATCH_A(s, fn, ...) ((s)->dtype == FDTD_F32 ? ((s)->f32_arith ? fn<float, float>(__VA_ARGS__) : fn<float, double>(__VA_ARGS__)) : fn<double, double>(__VA_ARGS__))
 
 // ------------------------------------------------------------------------------------------------------
 // halo exchange (z-slab ring).  Plane -1 / plane nk of every array are the ghost planes.
@@ -575,7 +578,7 @@ static fdtd_status_t flush_pending(Solver* s) {
     if (!s->b_pending) return FDTD_OK;
     fdtd_status_t st = exchange_E_top(s);
     if (st != FDTD_OK) return st;
-    st = DISPATCH(s, launch_sweep, s, true, 1, 0);
+    st = DISPATCH_A(s, launch_sweep, s, true, 1, 0);
     if (st != FDTD_OK) return st;
     s->b_pending = false;
     s->ghosts_b_valid = false;
@@ -740,7 +743,7 @@ static fdtd_status_t advance_pml_pair(Solver* s, int n_half, int src2, double am
         if (hi <= lo) { lo = lo2; hi = hi2; lo2 = hi2 = 0; }
         if (hi2 <= lo2) lo2 = hi2 = 0;
         if (hi <= lo) return FDTD_OK;
-        return DISPATCH(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2, halo_seq);
+        return DISPATCH_A(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2, halo_seq);
     };
     // slab ranks: ring exchange of the two ghost planes per side (+ J) overlapped with the interior planes, as in the
     // periodic solver; single GPU: one launch
@@ -749,19 +752,19 @@ static fdtd_status_t advance_pml_pair(Solver* s, int n_half, int src2, double am
     if (st != FDTD_OK) return st;
     int lo[3], hi[3];
     shrink_box(s, 2, 2 * V, lo, hi);
-    if ((st = DISPATCH(s, launch_rim_sweep, s, true, n_half, lo, hi, false)) != FDTD_OK) return st;
+    if ((st = DISPATCH_A(s, launch_rim_sweep, s, true, n_half, lo, hi, false)) != FDTD_OK) return st;
     if ((st = exchange_pair_planes(s, true, s->cur)) != FDTD_OK) return st;          // B1 top plane -> upper rank's plane -1
     shrink_box(s, 1, V, lo, hi);
-    if ((st = DISPATCH(s, launch_rim_sweep, s, false, 0, lo, hi, false)) != FDTD_OK) return st;
+    if ((st = DISPATCH_A(s, launch_rim_sweep, s, false, 0, lo, hi, false)) != FDTD_OK) return st;
     if ((st = exchange_pair_planes(s, false, s->cur)) != FDTD_OK) return st;         // E1 bottom plane -> lower rank's plane nk
     if (src2) {
         // the rim may meet the source box: the second step's sweeps read J from the arrays
         if ((st = DISPATCH(s, launch_source, s, amp2, 0)) != FDTD_OK) return st;
     }
     shrink_box(s, 0, 0, lo, hi);
-    if ((st = DISPATCH(s, launch_rim_sweep, s, true, 2, lo, hi, true)) != FDTD_OK) return st;
+    if ((st = DISPATCH_A(s, launch_rim_sweep, s, true, 2, lo, hi, true)) != FDTD_OK) return st;
     if ((st = exchange_pair_planes(s, true, s->cur ^ 1)) != FDTD_OK) return st;      // B2 top plane (new generation)
-    if ((st = DISPATCH(s, launch_rim_sweep, s, false, 0, lo, hi, true)) != FDTD_OK) return st;
+    if ((st = DISPATCH_A(s, launch_rim_sweep, s, false, 0, lo, hi, true)) != FDTD_OK) return st;
     return FDTD_OK;
 }
 
@@ -802,12 +805,20 @@ static fdtd_status_t advance(Solver* s, int remaining, int* done) {
             const int src2 = s->src_active ? 1 : 0;
             const double amp2 = src2 ? s->src_amp[s->src_t] : 0.0;
             st = overlapped(s, s->ghosts_t2_valid, true,
-                            [&](int lo, int hi, int lo2, int hi2, unsigned halo_seq) { return DISPATCH(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2, halo_seq); },
+                            [&](int lo, int hi, int lo2, int hi2, unsigned halo_seq) { return DISPATCH_A(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2, halo_seq); },
                             [&](cudaStream_t q, bool wait, cudaEvent_t e0, cudaEvent_t e1) { return exchange_t2(s, q, wait, e0, e1); });
             if (st != FDTD_OK) return st;
             if (src2) { s->src_t++; s->j_stale = true; }
             s->passes_t2++;
             *done = 2;
+        } else if (s->f32_arith) {
+            // the one-step fused kernels exist in double arithmetic only: a single step runs the two sweeps in place
+            if ((st = exchange_E_top(s)) != FDTD_OK) return st;
+            if ((st = DISPATCH_A(s, launch_sweep, s, true, n_half, 1)) != FDTD_OK) return st;
+            s->ghosts_b_valid = false;
+            if ((st = exchange_B_bottom(s)) != FDTD_OK) return st;
+            if ((st = DISPATCH_A(s, launch_sweep, s, false, 0, 0)) != FDTD_OK) return st;
+            s->cur ^= 1;   // (undone below: the sweeps work in place on the live generation)
         } else {
             st = overlapped(s, s->ghosts_fused_valid, false,
                             [&](int lo, int hi, int lo2, int hi2, unsigned) {
@@ -822,12 +833,12 @@ static fdtd_status_t advance(Solver* s, int remaining, int* done) {
     } else {
         st = exchange_E_top(s);
         if (st != FDTD_OK) return st;
-        st = DISPATCH(s, launch_sweep, s, true, n_half, 1);
+        st = DISPATCH_A(s, launch_sweep, s, true, n_half, 1);
         if (st != FDTD_OK) return st;
         s->ghosts_b_valid = false;
         st = exchange_B_bottom(s);
         if (st != FDTD_OK) return st;
-        st = DISPATCH(s, launch_sweep, s, false, 0, 0);
+        st = DISPATCH_A(s, launch_sweep, s, false, 0, 0);
         if (st != FDTD_OK) return st;
     }
     invalidate_ghosts(s);
@@ -908,6 +919,10 @@ static fdtd_status_t create_impl(const fdtd_config_t* cfg, Solver** out) {
     s->device = dev;
     s->dtype = cfg->dtype;
     s->esz = (cfg->dtype == FDTD_F32) ? 4 : 8;
+    if (cfg->flags & FDTD_FLAG_F32_ARITH) {
+        if (cfg->dtype != FDTD_F32) { delete s; return fail(FDTD_ERR_BAD_ARGUMENT, "FDTD_FLAG_F32_ARITH needs dtype FDTD_F32"); }
+        s->f32_arith = true;
+    }
 
     int k_begin, k_end;
     fdtd_slab_range_cfg(cfg, cfg->rank, &k_begin, &k_end);
@@ -1478,6 +1493,7 @@ fdtd_status_t fdtd_get_info(fdtd_solver_t* h, fdtd_info_t* info) {
     info->passes_t2 = s->passes_t2;
     info->transport = s->cfg.nranks <= 1 ? 0 : (s->peer ? 2 : (s->comm ? 1 : 0));
     info->halo_in_kernel = (s->peer && s->halo_in_kernel) ? 1 : 0;
+    info->f32_arith = s->f32_arith ? 1 : 0;
     return FDTD_OK;
 }
 

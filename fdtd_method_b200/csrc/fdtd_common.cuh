@@ -71,10 +71,35 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 
+// float arithmetic (FDTD_FLAG_F32_ARITH): same association, every operation rounded to float, never contracted
+__device__ __forceinline__ float dadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float dsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dmul(float a, float b) { return __fmul_rn(a, b); }
+
+// The two curl terms of the main-cell updates.
+//   curl2  : c1*d1 - c2*d2                      (B update, FDTD.cpp:121-126)
+//   curl2j : (cJ*j + c1*d1) - c2*d2             (E update, FDTD.cpp:85-93; use_j false: the current term is skipped,
+//                                                exact because J = +0.0 there)
+// double: the reference's operations, one rounding each.  float (FDTD_FLAG_F32_ARITH): explicit fused multiply-adds,
+// fma(c1, d1, -(c2*d2)) and fma(-c2, d2, fma(c1, d1, cJ*j)) -- two roundings fewer per component, which keeps the mode
+// inside 1e-5 relative L-inf of the fp64 reference (the CPU checker restates exactly this form for the mode).
+__device__ __forceinline__ double curl2(double c1, double d1, double c2, double d2) { return dsub(dmul(c1, d1), dmul(c2, d2)); }
+__device__ __forceinline__ float curl2(float c1, float d1, float c2, float d2) { return __fmaf_rn(c1, d1, -__fmul_rn(c2, d2)); }
+__device__ __forceinline__ double curl2j(double c1, double d1, double c2, double d2, double cj, double j, bool use_j) {
+    double t = dmul(c1, d1);
+    if (use_j) t = dadd(dmul(cj, j), t);
+    return dsub(t, dmul(c2, d2));
+}
+__device__ __forceinline__ float curl2j(float c1, float d1, float c2, float d2, float cj, float j, bool use_j) {
+    const float t = use_j ? __fmaf_rn(c1, d1, __fmul_rn(cj, j)) : __fmul_rn(c1, d1);
+    return __fmaf_rn(-c2, d2, t);
+}
+
 // One rounding to the storage type (fp32 mode: "float storage, double arithmetic").
 template <typename T> __device__ __forceinline__ double round_store(double x);
 template <> __device__ __forceinline__ double round_store<double>(double x) { return x; }
 template <> __device__ __forceinline__ double round_store<float>(double x) { return (double)__double2float_rn(x); }
+template <typename T> __device__ __forceinline__ float round_store(float x) { return x; }   // float arithmetic: already rounded
 
 // ---- 128-bit vector access -----------------------------------------------------------------------
 __device__ __forceinline__ void ldv(const double* p, double (&o)[2]) {
@@ -89,8 +114,15 @@ __device__ __forceinline__ void ldv(const float* p, double (&o)[2]) {   // 2 cel
     const float2 v = *reinterpret_cast<const float2*>(p);
     o[0] = (double)v.x; o[1] = (double)v.y;
 }
-__device__ __forceinline__ double lds1(const double* p) { return *p; }
-__device__ __forceinline__ double lds1(const float* p) { return (double)*p; }
+template <typename A, typename T> __device__ __forceinline__ A lds1(const T* p) { return (A)*p; }
+__device__ __forceinline__ void ldv(const float* p, float (&o)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void ldv(const float* p, float (&o)[2]) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    o[0] = v.x; o[1] = v.y;
+}
 
 // Store V values; `nvalid` < V only in the last vector of a row whose Ni is not a multiple of V.
 __device__ __forceinline__ void stv(double* p, const double (&v)[2], int nvalid) {
@@ -106,6 +138,18 @@ __device__ __forceinline__ void stv(float* p, const double (&v)[4], int nvalid) 
         *reinterpret_cast<float4*>(p) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
     } else {
         for (int e = 0; e < nvalid; ++e) p[e] = (float)v[e];
+    }
+}
+
+__device__ __forceinline__ void stv(float* p, const float (&v)[2], int nvalid) {
+    if (nvalid >= 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    else if (nvalid == 1) p[0] = v[0];
+}
+__device__ __forceinline__ void stv(float* p, const float (&v)[4], int nvalid) {
+    if (nvalid >= 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        for (int e = 0; e < nvalid; ++e) p[e] = v[e];
     }
 }
 

@@ -103,21 +103,24 @@ struct FusedT2Args {
 // ---- shared-memory plumbing ---------------------------------------------------------------------------------
 // Every shared access of a thread is [sa + compile-time offset] (one address register): exchange arrays are
 // (BY + 2) rows so that "one row up / down" is +-512 B with no clamping, the ring follows.
-constexpr int T2_V = 2;                  // cells per lane
-constexpr int T2_ROWB = FUSED_BX * 16;   // bytes per exchange row (32 lanes x 2 doubles)
+// A = arithmetic type: double for the two reference-faithful modes (fp64; fp32 storage with double arithmetic), float
+// for the opt-in FDTD_FLAG_F32_ARITH mode.  A lane always owns 16 bytes of registers per component and plane:
+template <typename A> __host__ __device__ constexpr int t2_v() { return 16 / (int)sizeof(A); }   // cells per lane: 2 / 4
+constexpr int T2_ROWB = FUSED_BX * 16;   // bytes per exchange row (32 lanes x 16 bytes of A)
 // Ring rows hold raw storage.  fp64: 64 cells = 512 B, the tile's footprint starts at byte 480*bx - 16 of a row.  fp32: the
 // footprint starts at byte 240*bx - 8, but a TMA box must start on a 16-byte boundary in global memory, so the box
 // starts 2 cells earlier and is 68 cells (272 B) wide; lane tx reads bytes [8 + 8 tx, 16 + 8 tx) of its ring row.
-template <typename T> __host__ __device__ constexpr int t2_rbox() { return sizeof(T) == 8 ? FUSED_BX * T2_V : FUSED_BX * T2_V + 4; }   // cells per ring row
-template <typename T> __host__ __device__ constexpr int t2_rskip() { return sizeof(T) == 8 ? 0 : 2; }                                  // cells before lane 0
-template <typename T> __host__ __device__ constexpr int t2_rrowb() { return t2_rbox<T>() * (int)sizeof(T); }                            // bytes per ring row
+// (float storage with float arithmetic: 4 cells = 16 bytes per lane, the fp64 layout again -- 128-cell boxes, no skip)
+template <typename T, typename A> __host__ __device__ constexpr int t2_rbox() { return sizeof(T) == sizeof(A) ? FUSED_BX * t2_v<A>() : FUSED_BX * t2_v<A>() + 4; }   // cells per ring row
+template <typename T, typename A> __host__ __device__ constexpr int t2_rskip() { return sizeof(T) == sizeof(A) ? 0 : 2; }                                            // cells before lane 0
+template <typename T, typename A> __host__ __device__ constexpr int t2_rrowb() { return t2_rbox<T, A>() * (int)sizeof(T); }                                          // bytes per ring row
 template <int BY> __host__ __device__ constexpr int t2_xq(int q) { return q * (BY + 2) * T2_ROWB; }          // exchange array q, own slot
 template <int BY> __host__ __device__ constexpr int t2_ringbase() { return 8 * (BY + 2) * T2_ROWB; }         // absolute offset of ring slot 0 comp 0
 constexpr int T2_D = 3;                  // ring depth = unroll factor of the k loop
-template <typename T, int BY> __host__ __device__ constexpr int t2_mbar0() { return t2_ringbase<BY>() + T2_D * 6 * BY * t2_rrowb<T>(); }   // absolute
-template <typename T, int BY>
+template <typename T, typename A, int BY> __host__ __device__ constexpr int t2_mbar0() { return t2_ringbase<BY>() + T2_D * 6 * BY * t2_rrowb<T, A>(); }   // absolute
+template <typename T, typename A, int BY>
 constexpr size_t fused_t2_smem_bytes() {
-    return (size_t)t2_mbar0<T, BY>() + 64;
+    return (size_t)t2_mbar0<T, A, BY>() + 64;
 }
 
 // ---- mbarrier / TMA primitives --------------------------------------------------------------------------------
@@ -143,8 +146,9 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm,
                  ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
-// Exchange arrays: always doubles.
-struct XIO {
+// Exchange arrays: 16 bytes of A per lane.
+template <typename A> struct XIO;
+template <> struct XIO<double> {
     template <int OFF> static __device__ __forceinline__ void ld(unsigned a, double (&v)[2]) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v[0]), "=d"(v[1]) : "r"(a), "n"(OFF) : "memory");
     }
@@ -152,21 +156,30 @@ struct XIO {
         asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v[0]), "d"(v[1]) : "memory");
     }
 };
-// Ring: raw storage, converted once on the way into registers.
-template <typename T> struct RingIO;
-template <> struct RingIO<double> {
-    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, double (&v)[2]) {
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v[0]), "=d"(v[1]) : "r"(a), "n"(OFF) : "memory");
+template <> struct XIO<float> {
+    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, float (&v)[4]) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a), "n"(OFF) : "memory");
+    }
+    template <int OFF> static __device__ __forceinline__ void st(unsigned a, const float (&v)[4]) {
+        asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
     }
 };
-template <> struct RingIO<float> {
+// Ring: raw storage, converted once on the way into registers.
+template <typename T, typename A> struct RingIO;
+template <> struct RingIO<double, double> {
+    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, double (&v)[2]) { XIO<double>::ld<OFF>(a, v); }
+};
+template <> struct RingIO<float, float> {
+    template <int OFF> static __device__ __forceinline__ void ld(unsigned a, float (&v)[4]) { XIO<float>::ld<OFF>(a, v); }
+};
+template <> struct RingIO<float, double> {
     template <int OFF> static __device__ __forceinline__ void ld(unsigned a, double (&v)[2]) {
         float f0, f1;
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(f0), "=f"(f1) : "r"(a), "n"(OFF) : "memory");
         v[0] = (double)f0; v[1] = (double)f1;
     }
 };
-// Global memory: 2 cells of storage type <-> 2 doubles.
+// Global memory: one lane's cells of storage type <-> registers of arithmetic type.
 __device__ __forceinline__ void t2_ldg(const double* p, double (&o)[2]) {
     const double2 v = *reinterpret_cast<const double2*>(p);
     o[0] = v.x; o[1] = v.y;
@@ -175,6 +188,10 @@ __device__ __forceinline__ void t2_ldg(const float* p, double (&o)[2]) {
     const float2 v = *reinterpret_cast<const float2*>(p);
     o[0] = (double)v.x; o[1] = (double)v.y;
 }
+__device__ __forceinline__ void t2_ldg(const float* p, float (&o)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
 template <bool CS> __device__ __forceinline__ void t2_stg(double* p, const double (&o)[2]) {
     if (CS) __stcs(reinterpret_cast<double2*>(p), make_double2(o[0], o[1]));
     else *reinterpret_cast<double2*>(p) = make_double2(o[0], o[1]);
@@ -182,6 +199,10 @@ template <bool CS> __device__ __forceinline__ void t2_stg(double* p, const doubl
 template <bool CS> __device__ __forceinline__ void t2_stg(float* p, const double (&o)[2]) {   // values are already float-representable
     if (CS) __stcs(reinterpret_cast<float2*>(p), make_float2((float)o[0], (float)o[1]));
     else *reinterpret_cast<float2*>(p) = make_float2((float)o[0], (float)o[1]);
+}
+template <bool CS> __device__ __forceinline__ void t2_stg(float* p, const float (&o)[4]) {
+    if (CS) __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
+    else *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // B += n_half * h(E)   (FDTD.cpp:121-126).  e = E(k), ek = E(k+1), (ezu, exu) = Ez, Ex one row up,
@@ -194,6 +215,7 @@ template <bool CS> __device__ __forceinline__ void t2_stg(float* p, const double
 #ifndef FDTD_T2_F32_MAGIC
 #define FDTD_T2_F32_MAGIC 0   // build-time switch (fdtd_method_b200/build.py: FDTD_T2_F32_MAGIC=1 in the environment)
 #endif
+template <typename T> __device__ __forceinline__ float t2_round(float x) { return x; }   // float arithmetic: every operation already rounds to float
 template <typename T>
 __device__ __forceinline__ double t2_round(double x) {
     if (sizeof(T) == 8) return x;
@@ -206,23 +228,22 @@ __device__ __forceinline__ double t2_round(double x) {
     return __dsub_rn(__dadd_rn(x, M), M);
 }
 
-template <typename T>
-__device__ __forceinline__ void t2_update_B(double (&b)[3][T2_V], const double (&e)[3][T2_V], const double (&ek)[3][T2_V],
-                                            const double (&ezu)[T2_V], const double (&exu)[T2_V], const double ez_nl,
-                                            const double ey_nl, const double cBx, const double cBy, const double cBz,
+template <typename T, typename A, int V>
+__device__ __forceinline__ void t2_update_B(A (&b)[3][V], const A (&e)[3][V], const A (&ek)[3][V],
+                                            const A (&ezu)[V], const A (&exu)[V], const A ez_nl,
+                                            const A ey_nl, const A cBx, const A cBy, const A cBz,
                                             const bool two) {
-    constexpr int V = T2_V;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
-        const double ex = e[0][q], ey = e[1][q], ez = e[2][q];
-        const double ezr = (q == V - 1) ? ez_nl : e[2][(q + 1) % V];
-        const double eyr = (q == V - 1) ? ey_nl : e[1][(q + 1) % V];
-        const double hx = dsub(dmul(cBz, dsub(ek[1][q], ey)), dmul(cBy, dsub(ezu[q], ez)));
-        const double hy = dsub(dmul(cBx, dsub(ezr, ez)), dmul(cBz, dsub(ek[0][q], ex)));
-        const double hz = dsub(dmul(cBy, dsub(exu[q], ex)), dmul(cBx, dsub(eyr, ey)));
-        double nbx = t2_round<T>(dadd(b[0][q], hx));
-        double nby = t2_round<T>(dadd(b[1][q], hy));
-        double nbz = t2_round<T>(dadd(b[2][q], hz));
+        const A ex = e[0][q], ey = e[1][q], ez = e[2][q];
+        const A ezr = (q == V - 1) ? ez_nl : e[2][(q + 1) % V];
+        const A eyr = (q == V - 1) ? ey_nl : e[1][(q + 1) % V];
+        const A hx = curl2(cBz, dsub(ek[1][q], ey), cBy, dsub(ezu[q], ez));
+        const A hy = curl2(cBx, dsub(ezr, ez), cBz, dsub(ek[0][q], ex));
+        const A hz = curl2(cBy, dsub(exu[q], ex), cBx, dsub(eyr, ey));
+        A nbx = t2_round<T>(dadd(b[0][q], hx));
+        A nby = t2_round<T>(dadd(b[1][q], hy));
+        A nbz = t2_round<T>(dadd(b[2][q], hz));
         if (two) {
             nbx = t2_round<T>(dadd(nbx, hx));
             nby = t2_round<T>(dadd(nby, hy));
@@ -234,28 +255,20 @@ __device__ __forceinline__ void t2_update_B(double (&b)[3][T2_V], const double (
 
 // E += g(B, J)   (FDTD.cpp:85-93 / kokkos_functors.h:81-89), in place.  b = B(k), (bxk, byk) = Bx, By at k-1,
 // (bzd, bxd) = Bz, Bx one row down, (bz_pl, by_pl) = Bz, By last element of the previous lane.
-template <typename T>
-__device__ __forceinline__ void t2_update_E(double (&e)[3][T2_V], const double (&b)[3][T2_V], const double (&bxk)[T2_V],
-                                            const double (&byk)[T2_V], const double (&bzd)[T2_V], const double (&bxd)[T2_V],
-                                            const double bz_pl, const double by_pl, const double cEx, const double cEy,
-                                            const double cEz, const double cJ, const bool use_j, const double (&jv)[3][T2_V]) {
-    constexpr int V = T2_V;
+template <typename T, typename A, int V>
+__device__ __forceinline__ void t2_update_E(A (&e)[3][V], const A (&b)[3][V], const A (&bxk)[V],
+                                            const A (&byk)[V], const A (&bzd)[V], const A (&bxd)[V],
+                                            const A bz_pl, const A by_pl, const A cEx, const A cEy,
+                                            const A cEz, const A cJ, const bool use_j, const A (&jv)[3][V]) {
 #pragma unroll
     for (int q = 0; q < V; ++q) {
-        const double bx = b[0][q], by = b[1][q], bz = b[2][q];
-        const double bzl = (q == 0) ? bz_pl : b[2][(q + V - 1) % V];
-        const double byl = (q == 0) ? by_pl : b[1][(q + V - 1) % V];
-        double tx_ = dmul(cEy, dsub(bz, bzd[q]));
-        double ty_ = dmul(cEz, dsub(bx, bxk[q]));
-        double tz_ = dmul(cEx, dsub(by, byl));
-        if (use_j) {
-            tx_ = dadd(dmul(cJ, jv[0][q]), tx_);
-            ty_ = dadd(dmul(cJ, jv[1][q]), ty_);
-            tz_ = dadd(dmul(cJ, jv[2][q]), tz_);
-        }
-        e[0][q] = t2_round<T>(dadd(e[0][q], dsub(tx_, dmul(cEz, dsub(by, byk[q])))));
-        e[1][q] = t2_round<T>(dadd(e[1][q], dsub(ty_, dmul(cEx, dsub(bz, bzl)))));
-        e[2][q] = t2_round<T>(dadd(e[2][q], dsub(tz_, dmul(cEy, dsub(bx, bxd[q])))));
+        const A bx = b[0][q], by = b[1][q], bz = b[2][q];
+        const A bzl = (q == 0) ? bz_pl : b[2][(q + V - 1) % V];
+        const A byl = (q == 0) ? by_pl : b[1][(q + V - 1) % V];
+        const A jx = use_j ? jv[0][q] : (A)0, jy = use_j ? jv[1][q] : (A)0, jz = use_j ? jv[2][q] : (A)0;
+        e[0][q] = t2_round<T>(dadd(e[0][q], curl2j(cEy, dsub(bz, bzd[q]), cEz, dsub(by, byk[q]), cJ, jx, use_j)));
+        e[1][q] = t2_round<T>(dadd(e[1][q], curl2j(cEz, dsub(bx, bxk[q]), cEx, dsub(bz, bzl), cJ, jy, use_j)));
+        e[2][q] = t2_round<T>(dadd(e[2][q], curl2j(cEx, dsub(by, byl), cEy, dsub(bx, bxd[q]), cJ, jz, use_j)));
     }
 }
 
@@ -316,40 +329,40 @@ __device__ __forceinline__ long long t2_plane_of(const FusedT2Args<T>& a, int k)
     return (long long)k * a.g.plane;
 }
 
-// One lane's 2 cells of one ring row: 16 bytes (fp64, L1 bypass) or 8 bytes (fp32).
-template <typename T, int OFF>
+// One lane's cells of one ring row: 16 bytes (L1 bypass) or 8 bytes (float storage, double arithmetic).
+template <typename T, typename A, int OFF>
 __device__ __forceinline__ void t2_cp_async_at(unsigned a, const T* gmem_src) {
-    if (sizeof(T) == 8) asm volatile("cp.async.cg.shared.global [%0+%1], [%2], 16;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
+    if (sizeof(T) == sizeof(A)) asm volatile("cp.async.cg.shared.global [%0+%1], [%2], 16;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0+%1], [%2], 8;\n" ::"r"(a), "n"(OFF), "l"(gmem_src) : "memory");
 }
 
 // Asynchronous copies (LDGSTS) of plane iteration kk into ring slot SLOT: old E(kk+1) and, for the rows
 // that produce B1, B0(kk).  Every thread copies the six vectors it will read back itself, so the ring needs no
 // barrier, only cp.async.wait_group.
-template <typename T, int BY, int SLOT>
+template <typename T, typename A, int BY, int SLOT>
 __device__ __forceinline__ void t2_issue_slot(const FusedT2Args<T>& a, const T2Ctx<T>& c, const int kk) {
-    constexpr int COMPB = BY * t2_rrowb<T>(), SLOTB = 6 * COMPB;
+    constexpr int COMPB = BY * t2_rrowb<T, A>(), SLOTB = 6 * COMPB;
     constexpr int RING = SLOT * SLOTB;
     if (c.ldE) {
         const long long pe = t2_plane_of(a, kk + 1) + c.roff;
-        t2_cp_async_at<T, RING + 0 * COMPB>(c.sr, a.Ein[0] + pe);
-        t2_cp_async_at<T, RING + 1 * COMPB>(c.sr, a.Ein[1] + pe);
-        t2_cp_async_at<T, RING + 2 * COMPB>(c.sr, a.Ein[2] + pe);
+        t2_cp_async_at<T, A, RING + 0 * COMPB>(c.sr, a.Ein[0] + pe);
+        t2_cp_async_at<T, A, RING + 1 * COMPB>(c.sr, a.Ein[1] + pe);
+        t2_cp_async_at<T, A, RING + 2 * COMPB>(c.sr, a.Ein[2] + pe);
         if (c.needB1) {
             const long long pb = t2_plane_of(a, kk) + c.roff;
-            t2_cp_async_at<T, RING + 3 * COMPB>(c.sr, a.Bin[0] + pb);
-            t2_cp_async_at<T, RING + 4 * COMPB>(c.sr, a.Bin[1] + pb);
-            t2_cp_async_at<T, RING + 5 * COMPB>(c.sr, a.Bin[2] + pb);
+            t2_cp_async_at<T, A, RING + 3 * COMPB>(c.sr, a.Bin[0] + pb);
+            t2_cp_async_at<T, A, RING + 4 * COMPB>(c.sr, a.Bin[1] + pb);
+            t2_cp_async_at<T, A, RING + 5 * COMPB>(c.sr, a.Bin[2] + pb);
         }
     }
 }
 
 // TMA flavour of the ring fill (tiles that need no periodic wrap in i / j): one thread issues six tensor copies, each
 // a {t2_rbox cells, BY rows, 1 plane} box that lands in the slot with exactly the ring's [row][lane] layout.
-template <typename T, int BY, int SLOT>
+template <typename T, typename A, int BY, int SLOT>
 __device__ __forceinline__ void t2_issue_slot_tma(const FusedT2Args<T>& a, const unsigned smem0, const int x, const int y, const int kk) {
-    constexpr int COMPB = BY * t2_rrowb<T>(), SLOTB = 6 * COMPB;
-    const unsigned bar = smem0 + (unsigned)(t2_mbar0<T, BY>() + 8 * SLOT);
+    constexpr int COMPB = BY * t2_rrowb<T, A>(), SLOTB = 6 * COMPB;
+    const unsigned bar = smem0 + (unsigned)(t2_mbar0<T, A, BY>() + 8 * SLOT);
     const unsigned dst = smem0 + (unsigned)(t2_ringbase<BY>() + SLOT * SLOTB);
     int ke = kk + 1, kb = kk;
     if (a.g.wrap_k) {
@@ -359,40 +372,40 @@ __device__ __forceinline__ void t2_issue_slot_tma(const FusedT2Args<T>& a, const
     mbar_arrive_expect_tx(bar, (unsigned)(6 * COMPB));
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-        tma_load_3d(dst + q * COMPB, &a.tmE[q], x - t2_rskip<T>(), y, ke + GHOST_PLANES, bar);
-        tma_load_3d(dst + (3 + q) * COMPB, &a.tmB[q], x - t2_rskip<T>(), y, kb + GHOST_PLANES, bar);
+        tma_load_3d(dst + q * COMPB, &a.tmE[q], x - t2_rskip<T, A>(), y, ke + GHOST_PLANES, bar);
+        tma_load_3d(dst + (3 + q) * COMPB, &a.tmB[q], x - t2_rskip<T, A>(), y, kb + GHOST_PLANES, bar);
     }
 }
 
 // One plane iteration.  Register sets by role on entry:
 //   en : free -> old E(k+1)           e0 : old E(k) -> E1(k)          e1 : E1(k-1) -> E2(k-1) (stored)
 //   b  : free -> B0(k) -> B1(k)        b1 : B1(k-1) -> B2(k-1) (stored)  b2 : B2(k-2) (x, y used)
-template <typename T, int BY, bool TWO_A, bool HAS_J, bool TMA, int ABL, int SLOT>
+template <typename T, typename A, int BY, bool TWO_A, bool HAS_J, bool TMA, int ABL, int SLOT>
 __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>& c, const int k, const unsigned parity,
-                                         double (&en)[3][T2_V], double (&e0)[3][T2_V], double (&e1)[3][T2_V],
-                                         double (&b)[3][T2_V], double (&b1)[3][T2_V], double (&b2)[3][T2_V]) {
-    constexpr int V = T2_V;
+                                         A (&en)[3][t2_v<A>()], A (&e0)[3][t2_v<A>()], A (&e1)[3][t2_v<A>()],
+                                         A (&b)[3][t2_v<A>()], A (&b1)[3][t2_v<A>()], A (&b2)[3][t2_v<A>()]) {
+    constexpr int V = t2_v<A>();
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int UP = T2_ROWB, DN = -T2_ROWB;
     constexpr int XE0z = t2_xq<BY>(0), XE0x = t2_xq<BY>(1), XB1z = t2_xq<BY>(2), XB1x = t2_xq<BY>(3);
     constexpr int XE1z = t2_xq<BY>(4), XE1x = t2_xq<BY>(5), XB2z = t2_xq<BY>(6), XB2x = t2_xq<BY>(7);
-    constexpr int COMPB = BY * t2_rrowb<T>(), SLOTB = 6 * COMPB;
+    constexpr int COMPB = BY * t2_rrowb<T, A>(), SLOTB = 6 * COMPB;
     constexpr int RING = SLOT * SLOTB;                 // relative to c.sr
     constexpr int NEXT = (SLOT + T2_D - 1) % T2_D;     // slot freed by the previous plane
-    using IO = XIO;
-    using RIO = RingIO<T>;
+    using IO = XIO<A>;
+    using RIO = RingIO<T, A>;
     const unsigned sa = c.sa, sr = c.sr;
-    const double cBx = a.c.cBx, cBy = a.c.cBy, cBz = a.c.cBz;
-    const double cEx = a.c.cEx, cEy = a.c.cEy, cEz = a.c.cEz, cJ = a.c.cJ;
+    const A cBx = (A)a.c.cBx, cBy = (A)a.c.cBy, cBz = (A)a.c.cBz;
+    const A cEx = (A)a.c.cEx, cEy = (A)a.c.cEy, cEz = (A)a.c.cEz, cJ = (A)a.c.cJ;
 
     // ================= phase X: B1(k) =============================================================================
     if (TMA) {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
-        if (c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, BY, NEXT>(a, smem0, c.tile_x, c.tile_y, k + T2_D - 1);
-        mbar_wait(smem0 + (unsigned)(t2_mbar0<T, BY>() + 8 * SLOT), parity);
+        if (c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, A, BY, NEXT>(a, smem0, c.tile_x, c.tile_y, k + T2_D - 1);
+        mbar_wait(smem0 + (unsigned)(t2_mbar0<T, A, BY>() + 8 * SLOT), parity);
     } else {
-        if (k + T2_D - 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, NEXT>(a, c, k + T2_D - 1);
+        if (k + T2_D - 1 <= c.ke && ABL != 3) t2_issue_slot<T, A, BY, NEXT>(a, c, k + T2_D - 1);
         cp_async_commit();
         cp_async_wait<T2_D - 1>();
     }
@@ -403,12 +416,12 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
         RIO::template ld<RING + 3 * COMPB>(sr, b[0]);
         RIO::template ld<RING + 4 * COMPB>(sr, b[1]);
         RIO::template ld<RING + 5 * COMPB>(sr, b[2]);
-        double ezu[V], exu[V];
+        A ezu[V], exu[V];
         IO::template ld<XE0z + UP>(sa, ezu);
         IO::template ld<XE0x + UP>(sa, exu);
-        const double ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
-        const double ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
-        if (ABL != 4) t2_update_B<T>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, TWO_A);
+        const A ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
+        const A ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
+        if (ABL != 4) t2_update_B<T, A, V>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, TWO_A);
         IO::template st<XB1z>(sa, b[2]);
         IO::template st<XB1x>(sa, b[0]);
     }
@@ -418,11 +431,11 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     IO::template st<XE0z>(sa, en[2]);   // old E(k+1) rows for the next plane's phase X
     IO::template st<XE0x>(sa, en[0]);
     if (c.needE1) {
-        double bzd[V], bxd[V], jv[3][V];
+        A bzd[V], bxd[V], jv[3][V];
         IO::template ld<XB1z + DN>(sa, bzd);
         IO::template ld<XB1x + DN>(sa, bxd);
-        const double bz_pl = __shfl_up_sync(FULL, b[2][V - 1], 1);
-        const double by_pl = __shfl_up_sync(FULL, b[1][V - 1], 1);
+        const A bz_pl = __shfl_up_sync(FULL, b[2][V - 1], 1);
+        const A by_pl = __shfl_up_sync(FULL, b[1][V - 1], 1);
         bool use_j = false;
         if (HAS_J) {
             // J of step s applies to E1(k) on owned planes and on the halo planes that recompute a neighbour's
@@ -438,16 +451,16 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
             }
         }
         // e0 (= old E(k)) becomes E1(k) in place
-        if (ABL != 4) t2_update_E<T>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+        if (ABL != 4) t2_update_E<T, A, V>(e0, b, b1[0], b1[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
     }
     if (c.needB2) {
-        double ezu[V], exu[V];
+        A ezu[V], exu[V];
         IO::template ld<XE1z + UP>(sa, ezu);   // E1(k-1) one row up (written in phase Z of the previous plane)
         IO::template ld<XE1x + UP>(sa, exu);
-        const double ez_nl = __shfl_down_sync(FULL, e1[2][0], 1);
-        const double ey_nl = __shfl_down_sync(FULL, e1[1][0], 1);
+        const A ez_nl = __shfl_down_sync(FULL, e1[2][0], 1);
+        const A ey_nl = __shfl_down_sync(FULL, e1[1][0], 1);
         // b1 (= B1(k-1)) becomes B2(k-1) in place
-        if (ABL != 4) t2_update_B<T>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
+        if (ABL != 4) t2_update_B<T, A, V>(b1, e1, e0, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, true);
         IO::template st<XB2z>(sa, b1[2]);
         IO::template st<XB2x>(sa, b1[0]);
     }
@@ -459,11 +472,11 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
         IO::template st<XE1x>(sa, e0[0]);
     }
     if (c.needE2) {
-        double bzd[V], bxd[V], jv[3][V];
+        A bzd[V], bxd[V], jv[3][V];
         IO::template ld<XB2z + DN>(sa, bzd);
         IO::template ld<XB2x + DN>(sa, bxd);
-        const double bz_pl = __shfl_up_sync(FULL, b1[2][V - 1], 1);
-        const double by_pl = __shfl_up_sync(FULL, b1[1][V - 1], 1);
+        const A bz_pl = __shfl_up_sync(FULL, b1[2][V - 1], 1);
+        const A by_pl = __shfl_up_sync(FULL, b1[1][V - 1], 1);
         const int kB = k - 1;                          // plane of stage B (an owned plane whenever it is stored)
         const bool stored = (kB >= c.kb);
         bool use_j = false;
@@ -481,7 +494,7 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
                     for (int q = 0; q < V; ++q) {
                         const int ii = c.i + q;
                         if (ii >= a.s_lo[0] && ii < a.s_hi[0]) {
-                            const double v = t2_round<T>(dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wy), wz));
+                            const A v = (A)t2_round<T>(dmul(dmul(dmul(a.amp2, a.sw[0][ii - a.s_lo[0]]), wy), wz));   // (double product, one rounding: source_kernel)
                             jv[0][q] = v; jv[1][q] = v; jv[2][q] = v;
                         }
                     }
@@ -489,7 +502,7 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
             }
         }
         // e1 (= E1(k-1)) becomes E2(k-1) in place
-        if (ABL != 4) t2_update_E<T>(e1, b1, b2[0], b2[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
+        if (ABL != 4) t2_update_E<T, A, V>(e1, b1, b2[0], b2[1], bzd, bxd, bz_pl, by_pl, cEx, cEy, cEz, cJ, use_j, jv);
         if (c.out && stored && ABL != 2) {
             const long long o = (long long)kB * a.g.plane + c.roff;
             if (a.st_cs) {
@@ -511,12 +524,12 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     }
 }
 
-template <typename T, int BY, bool TWO_A, bool HAS_J, bool TMA, int ABL>
+template <typename T, typename A, int BY, bool TWO_A, bool HAS_J, bool TMA, int ABL>
 __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
-    constexpr int V = T2_V;
+    constexpr int V = t2_v<A>();
     constexpr int TJU = BY - 4;               // output rows per CTA
     constexpr int TIU = FUSED_OUT_LANES * V;  // output cells per CTA row
-    using IO = XIO;
+    using IO = XIO<A>;
     static_assert(BY >= 5, "T2 pass needs at least one output row");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -525,8 +538,8 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     const int Ni = a.g.Ni, Nj = a.g.Nj;
     T2Ctx<T> c;
     c.sa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)((ty + 1) * T2_ROWB + tx * 16);   // the one shared-memory address register ...
-    if (sizeof(T) == 8) c.sr = c.sa + (unsigned)(t2_ringbase<BY>() - T2_ROWB);                          // ... (fp64: the ring is sa + constant)
-    else c.sr = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(t2_ringbase<BY>() + ty * t2_rrowb<T>() + (t2_rskip<T>() + tx * T2_V) * (int)sizeof(T));
+    if (sizeof(T) == sizeof(A)) c.sr = c.sa + (unsigned)(t2_ringbase<BY>() - T2_ROWB);                  // ... (16 bytes of storage per lane: the ring is sa + constant)
+    else c.sr = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(t2_ringbase<BY>() + ty * t2_rrowb<T, A>() + (t2_rskip<T, A>() + tx * V) * (int)sizeof(T));
 
     // ---- roles ---------------------------------------------------------------------------------------------
     {
@@ -560,11 +573,11 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     c.j_ijB = c.j_ijA && c.out;
 
     // ---- register sets (rotating roles, see t2_plane) ----------------------------------------------------------
-    double eA[3][V], eB[3][V], eC[3][V], bA[3][V], bB[3][V], bC[3][V];
+    A eA[3][V], eB[3][V], eC[3][V], bA[3][V], bB[3][V], bC[3][V];
 #pragma unroll
     for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int v = 0; v < V; ++v) { eA[q][v] = eB[q][v] = eC[q][v] = 0.0; bA[q][v] = bB[q][v] = bC[q][v] = 0.0; }
+        for (int v = 0; v < V; ++v) { eA[q][v] = eB[q][v] = eC[q][v] = (A)0; bA[q][v] = bB[q][v] = bC[q][v] = (A)0; }
 
     // ---- prologue: the first two ring slots, old E(kb-2) and its rows ------------------------------------------------
     const int k_first = c.kb - 2;
@@ -572,16 +585,16 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
         const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
         if (c.producer) {
 #pragma unroll
-            for (int d = 0; d < T2_D; ++d) mbar_init(smem0 + (unsigned)(t2_mbar0<T, BY>() + 8 * d), 1);
+            for (int d = 0; d < T2_D; ++d) mbar_init(smem0 + (unsigned)(t2_mbar0<T, A, BY>() + 8 * d), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            t2_issue_slot_tma<T, BY, 0>(a, smem0, c.tile_x, c.tile_y, k_first);
-            if (k_first + 1 <= c.ke) t2_issue_slot_tma<T, BY, 1>(a, smem0, c.tile_x, c.tile_y, k_first + 1);
+            t2_issue_slot_tma<T, A, BY, 0>(a, smem0, c.tile_x, c.tile_y, k_first);
+            if (k_first + 1 <= c.ke) t2_issue_slot_tma<T, A, BY, 1>(a, smem0, c.tile_x, c.tile_y, k_first + 1);
         }
     } else {
-        if (ABL != 3) t2_issue_slot<T, BY, 0>(a, c, k_first);
+        if (ABL != 3) t2_issue_slot<T, A, BY, 0>(a, c, k_first);
         cp_async_commit();
-        if (k_first + 1 <= c.ke && ABL != 3) t2_issue_slot<T, BY, 1>(a, c, k_first + 1);
+        if (k_first + 1 <= c.ke && ABL != 3) t2_issue_slot<T, A, BY, 1>(a, c, k_first + 1);
         cp_async_commit();
     }
     if (c.ldE) {
@@ -597,11 +610,11 @@ __device__ __forceinline__ void fused_BE_T2_body(const FusedT2Args<T>& a) {
     unsigned parity = 0;
 #pragma unroll 1
     for (int k = k_first; k <= c.ke; k += 3) {
-        t2_plane<T, BY, TWO_A, HAS_J, TMA, ABL, 0>(a, c, k, parity, eA, eB, eC, bA, bB, bC);
+        t2_plane<T, A, BY, TWO_A, HAS_J, TMA, ABL, 0>(a, c, k, parity, eA, eB, eC, bA, bB, bC);
         if (k + 1 > c.ke) break;
-        t2_plane<T, BY, TWO_A, HAS_J, TMA, ABL, 1>(a, c, k + 1, parity, eC, eA, eB, bC, bA, bB);
+        t2_plane<T, A, BY, TWO_A, HAS_J, TMA, ABL, 1>(a, c, k + 1, parity, eC, eA, eB, bC, bA, bB);
         if (k + 2 > c.ke) break;
-        t2_plane<T, BY, TWO_A, HAS_J, TMA, ABL, 2>(a, c, k + 2, parity, eB, eC, eA, bB, bC, bA);
+        t2_plane<T, A, BY, TWO_A, HAS_J, TMA, ABL, 2>(a, c, k + 2, parity, eB, eC, eA, bB, bC, bA);
         parity ^= 1u;
     }
     if (!TMA) cp_async_wait<0>();
@@ -613,9 +626,9 @@ __device__ __forceinline__ bool t2_meets(int lo, int hi, int blo, int bhi, int N
     return (lo < bhi && hi > blo) || (lo < bhi - N && hi > blo - N) || (lo < bhi + N && hi > blo + N);
 }
 
-template <typename T, int BY, int MINB, bool TWO_A, int ABL = 0>
+template <typename T, typename A, int BY, int MINB, bool TWO_A, int ABL = 0>
 __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const __grid_constant__ FusedT2Args<T> a) {
-    constexpr int V = T2_V;
+    constexpr int V = t2_v<A>();
     // CTA-uniform: only the few tiles whose footprint (halo included) meets the box where J may be non-zero run
     // the loop that knows about currents; tiles that need no periodic wrap in i / j load through TMA.
     int tbx, tby;
@@ -643,11 +656,11 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
                        t2_meets(k0, k1, a.jbox.lo[2], a.jbox.hi[2], a.g.Nk);
     const bool tma = a.use_tma && ABL == 0 && i0 >= 0 && i0 + FUSED_BX * V <= a.g.Ni && j0 >= 0 && j0 + BY <= a.g.Nj;
     if (has_j) {
-        fused_BE_T2_body<T, BY, TWO_A, true, false, ABL>(a);   // (rare tiles: keep one flavour)
+        fused_BE_T2_body<T, A, BY, TWO_A, true, false, ABL>(a);   // (rare tiles: keep one flavour)
     } else if (tma) {
-        fused_BE_T2_body<T, BY, TWO_A, false, true, ABL>(a);
+        fused_BE_T2_body<T, A, BY, TWO_A, false, true, ABL>(a);
     } else {
-        fused_BE_T2_body<T, BY, TWO_A, false, false, ABL>(a);
+        fused_BE_T2_body<T, A, BY, TWO_A, false, false, ABL>(a);
     }
 }
 

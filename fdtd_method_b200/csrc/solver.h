@@ -41,6 +41,7 @@ struct Solver {
     int device = 0;
     int dtype = FDTD_F64;
     size_t esz = 8;
+    bool f32_arith = false;        // FDTD_FLAG_F32_ARITH: float storage AND float arithmetic (not a reference mode)
     Geom g{};
     Coefs c{};
     bool has_pml = false;

@@ -57,7 +57,8 @@ constexpr int SWEEP_BY = 8;   // rows along j
 // V = cells per thread: 16 bytes' worth by default; the float PML instantiation takes 2 (8-byte accesses, still whole
 // 32-byte sectors per 4 lanes) -- with 4 cells of double arithmetic plus split fields it needs 194-224 registers and
 // runs one CTA per SM.
-template <typename T, bool PML, int V = VecOf<T>::V>
+// A = arithmetic type (double; float only with FDTD_FLAG_F32_ARITH, where T = float too).
+template <typename T, bool PML, int V = VecOf<T>::V, typename A = double>
 __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const SweepArgs<T> a) {
     const int Ni = a.g.Ni, Nj = a.g.Nj;
     const int i0 = (blockIdx.x * SWEEP_BX + threadIdx.x) * V;
@@ -88,10 +89,10 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
     T* BxO = a.Bout[0];
     T* ByO = a.Bout[1];
     T* BzO = a.Bout[2];
-    const double cx = a.c.cBx, cy = a.c.cBy, cz = a.c.cBz;
+    const A cx = a.c.cBx, cy = a.c.cBy, cz = a.c.cBz;
 
     bool col_main[V];
-    double dcx[V], c2x[V];
+    A dcx[V], c2x[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
         col_main[e] = true;
@@ -104,14 +105,14 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
         }
     }
     bool jrow_main = true;
-    double dcy = 1.0, c2y = 0.0;
+    A dcy = 1.0, c2y = 0.0;
     if (PML) {
         jrow_main = (j >= a.p.lo[1] && j < a.p.hi[1]);
         dcy = a.p.decay[1][j];
         c2y = a.p.coef2[1][j];
     }
 
-    double ex[V], ey[V];
+    A ex[V], ey[V];
     {
         const long long o = (long long)kb * a.g.plane + row + i0;
         ldv(Ex + o, ex);
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
         }
 
         bool row_main = jrow_main;
-        double dcz = 1.0, c2z = 0.0;
+        A dcz = 1.0, c2z = 0.0;
         if (PML) {
             const int kg = a.g.k0 + k;
             row_main = row_main && (kg >= a.p.lo[2] && kg < a.p.hi[2]);
@@ -157,20 +158,20 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
             carry_ok = true;
         }
 
-        double exn[V], eyn[V], ez[V], ezj[V], exj[V], bx[V], by[V], bz[V];
+        A exn[V], eyn[V], ez[V], ezj[V], exj[V], bx[V], by[V], bz[V];
         ldv(Ex + pkn + row + i0, exn);
         ldv(Ey + pkn + row + i0, eyn);
         ldv(Ez + o, ez);
         ldv(Ez + pk + rown + i0, ezj);
         ldv(Ex + pk + rown + i0, exj);
-        const double ez_r = lds1(Ez + pk + row + cn);
-        const double ey_r = lds1(Ey + pk + row + cn);
+        const A ez_r = lds1<A>(Ez + pk + row + cn);
+        const A ey_r = lds1<A>(Ey + pk + row + cn);
         if (!all_pml) {   // a shell cell's B is the sum of its split fields (FDTD_PML.cpp:197-199): the old value is never read
             ldv(Bx + o, bx);
             ldv(By + o, by);
             ldv(Bz + o, bz);
         }
-        double sxy[V], sxz[V], syx[V], syz[V], szx[V], szy[V];
+        A sxy[V], sxz[V], syx[V], syz[V], szx[V], szy[V];
         if (PML && any_pml) {
             ldv(a.f.SB[S_XY] + o, sxy); ldv(a.f.SB[S_XZ] + o, sxz);
             ldv(a.f.SB[S_YX] + o, syx); ldv(a.f.SB[S_YZ] + o, syz);
@@ -181,19 +182,19 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
         for (int e = 0; e < V; ++e) {
             // right (i+1) neighbours: own next element, or the wrapped/next-thread scalar
             const bool use_scalar = (e == V - 1) || (i0 + e + 1 == Ni);
-            const double ezr = use_scalar ? ez_r : ez[(e + 1) % V];
-            const double eyr = use_scalar ? ey_r : ey[(e + 1) % V];
-            const double dEy_k = dsub(eyn[e], ey[e]);
-            const double dEz_j = dsub(ezj[e], ez[e]);
-            const double dEz_i = dsub(ezr, ez[e]);
-            const double dEx_k = dsub(exn[e], ex[e]);
-            const double dEx_j = dsub(exj[e], ex[e]);
-            const double dEy_i = dsub(eyr, ey[e]);
+            const A ezr = use_scalar ? ez_r : ez[(e + 1) % V];
+            const A eyr = use_scalar ? ey_r : ey[(e + 1) % V];
+            const A dEy_k = dsub(eyn[e], ey[e]);
+            const A dEz_j = dsub(ezj[e], ez[e]);
+            const A dEz_i = dsub(ezr, ez[e]);
+            const A dEx_k = dsub(exn[e], ex[e]);
+            const A dEx_j = dsub(exj[e], ex[e]);
+            const A dEy_i = dsub(eyr, ey[e]);
             if (!PML || (row_main && col_main[e])) {
                 // FDTD.cpp:121-126
-                const double hx = dsub(dmul(cz, dEy_k), dmul(cy, dEz_j));
-                const double hy = dsub(dmul(cx, dEz_i), dmul(cz, dEx_k));
-                const double hz = dsub(dmul(cy, dEx_j), dmul(cx, dEy_i));
+                const A hx = curl2(cz, dEy_k, cy, dEz_j);
+                const A hy = curl2(cx, dEz_i, cz, dEx_k);
+                const A hz = curl2(cy, dEx_j, cx, dEy_i);
                 if (a.n_half >= 1) {
                     bx[e] = round_store<T>(dadd(bx[e], hx));
                     by[e] = round_store<T>(dadd(by[e], hy));
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_B_kernel(const Swee
     }
 }
 
-template <typename T, bool PML, int V = VecOf<T>::V>
+template <typename T, bool PML, int V = VecOf<T>::V, typename A = double>
 __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const SweepArgs<T> a) {
     const int Ni = a.g.Ni, Nj = a.g.Nj;
     const int i0 = (blockIdx.x * SWEEP_BX + threadIdx.x) * V;
@@ -264,10 +265,10 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
     const T* __restrict__ Jx = a.f.J[0];
     const T* __restrict__ Jy = a.j_quirk ? a.f.J[0] : a.f.J[1];
     const T* __restrict__ Jz = a.j_quirk ? a.f.J[0] : a.f.J[2];
-    const double cx = a.c.cEx, cy = a.c.cEy, cz = a.c.cEz, cj = a.c.cJ;
+    const A cx = a.c.cEx, cy = a.c.cEy, cz = a.c.cEz, cj = a.c.cJ;
 
     bool col_main[V];
-    double dcx[V], c2x[V];
+    A dcx[V], c2x[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
         col_main[e] = true;
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
         }
     }
     bool jrow_main = true;
-    double dcy = 1.0, c2y = 0.0;
+    A dcy = 1.0, c2y = 0.0;
     if (PML) {
         jrow_main = (j >= a.p.lo[1] && j < a.p.hi[1]);
         dcy = a.p.decay[1][j];
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
     const bool j_ij = !a.jbox.empty() && (i0 < a.jbox.hi[0] && i0 + V > a.jbox.lo[0]) &&
                       (j >= a.jbox.lo[1] && j < a.jbox.hi[1]);
 
-    double bxm[V], bym[V];   // B at plane k-1
+    A bxm[V], bym[V];   // B at plane k-1
     {
         int km = kb - 1;
         if (km < 0 && a.g.wrap_k) km = a.g.nk - 1;
@@ -316,16 +317,16 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
             carry_ok = true;
         }
 
-        double bx[V], by[V], bz[V], bzj[V], bxj[V], e_x[V], e_y[V], e_z[V];
+        A bx[V], by[V], bz[V], bzj[V], bxj[V], e_x[V], e_y[V], e_z[V];
         ldv(Bx + o, bx);
         ldv(By + o, by);
         ldv(Bz + o, bz);
         ldv(Bz + pk + rowp + i0, bzj);
         ldv(Bx + pk + rowp + i0, bxj);
-        const double bz_l = lds1(Bz + pk + row + cp);
-        const double by_l = lds1(By + pk + row + cp);
+        const A bz_l = lds1<A>(Bz + pk + row + cp);
+        const A by_l = lds1<A>(By + pk + row + cp);
         bool row_main = jrow_main;
-        double dcz = 1.0, c2z = 0.0;
+        A dcz = 1.0, c2z = 0.0;
         if (PML) {
             row_main = row_main && (kg >= a.p.lo[2] && kg < a.p.hi[2]);
             dcz = a.p.decay[2][kg];
@@ -347,13 +348,13 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
         }
 
         const bool use_j = !all_pml && j_ij && (kg >= a.jbox.lo[2] && kg < a.jbox.hi[2]);
-        double jx[V], jy[V], jz[V];
+        A jx[V], jy[V], jz[V];
         if (use_j) {
             ldv(Jx + o, jx);
             ldv(Jy + o, jy);
             ldv(Jz + o, jz);
         }
-        double sxy[V], sxz[V], syx[V], syz[V], szx[V], szy[V];
+        A sxy[V], sxz[V], syx[V], syz[V], szx[V], szy[V];
         if (PML && any_pml) {
             ldv(a.f.SE[S_XY] + o, sxy); ldv(a.f.SE[S_XZ] + o, sxz);
             ldv(a.f.SE[S_YX] + o, syx); ldv(a.f.SE[S_YZ] + o, syz);
@@ -362,25 +363,20 @@ __global__ void __launch_bounds__(SWEEP_BX * SWEEP_BY) sweep_E_kernel(const Swee
 
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            const double bzl = (e == 0) ? bz_l : bz[(e + V - 1) % V];
-            const double byl = (e == 0) ? by_l : by[(e + V - 1) % V];
-            const double dBz_j = dsub(bz[e], bzj[e]);
-            const double dBy_k = dsub(by[e], bym[e]);
-            const double dBx_k = dsub(bx[e], bxm[e]);
-            const double dBz_i = dsub(bz[e], bzl);
-            const double dBy_i = dsub(by[e], byl);
-            const double dBx_j = dsub(bx[e], bxj[e]);
+            const A bzl = (e == 0) ? bz_l : bz[(e + V - 1) % V];
+            const A byl = (e == 0) ? by_l : by[(e + V - 1) % V];
+            const A dBz_j = dsub(bz[e], bzj[e]);
+            const A dBy_k = dsub(by[e], bym[e]);
+            const A dBx_k = dsub(bx[e], bxm[e]);
+            const A dBz_i = dsub(bz[e], bzl);
+            const A dBy_i = dsub(by[e], byl);
+            const A dBx_j = dsub(bx[e], bxj[e]);
             if (!PML || (row_main && col_main[e])) {
                 // FDTD.cpp:85-93 / kokkos_functors.h:81-89
-                double tx = dmul(cy, dBz_j), ty = dmul(cz, dBx_k), tz = dmul(cx, dBy_i);
-                if (use_j) {
-                    tx = dadd(dmul(cj, jx[e]), tx);
-                    ty = dadd(dmul(cj, jy[e]), ty);
-                    tz = dadd(dmul(cj, jz[e]), tz);
-                }
-                e_x[e] = dadd(e_x[e], dsub(tx, dmul(cz, dBy_k)));
-                e_y[e] = dadd(e_y[e], dsub(ty, dmul(cx, dBz_i)));
-                e_z[e] = dadd(e_z[e], dsub(tz, dmul(cy, dBx_j)));
+                const A vx = use_j ? jx[e] : (A)0, vy = use_j ? jy[e] : (A)0, vz = use_j ? jz[e] : (A)0;
+                e_x[e] = dadd(e_x[e], curl2j(cy, dBz_j, cz, dBy_k, cj, vx, use_j));
+                e_y[e] = dadd(e_y[e], curl2j(cz, dBx_k, cx, dBz_i, cj, vy, use_j));
+                e_z[e] = dadd(e_z[e], curl2j(cx, dBy_i, cy, dBx_j, cj, vz, use_j));
             } else {
                 // FDTD_PML.cpp:113-130
                 syx[e] = round_store<T>(dsub(dmul(syx[e], dcx[e]), dmul(c2x[e], dBz_i)));

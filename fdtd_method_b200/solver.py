@@ -52,7 +52,8 @@ class FDTD:
     """Periodic Yee solver on one B200 (or one z-slab rank of a multi-GPU ring)."""
 
     def __init__(self, parameters: Parameters, dt: float, *, dtype=np.float64, j_openmp_quirk: bool = False,
-                 fusion: bool = True, temporal: bool = True, overlap: bool = True, pml_split: bool = True, device: int = -1, rank: int = 0, nranks: int = 1,
+                 fusion: bool = True, temporal: bool = True, overlap: bool = True, pml_split: bool = True, f32_arith: bool = False, uniform_slabs: bool = False,
+                 device: int = -1, rank: int = 0, nranks: int = 1,
                  _pml_mode: int = _capi.PML_NONE, _pml_percent: float = 0.0, _pml_thickness=(0, 0, 0)):
         L = _capi.lib()
         cfg = _capi.Config()
@@ -65,7 +66,8 @@ class FDTD:
         cfg.dtype = _capi.F32 if self.dtype == np.float32 else _capi.F64
         cfg.flags = ((_capi.FLAG_J_OPENMP_QUIRK if j_openmp_quirk else 0) | (0 if fusion else _capi.FLAG_NO_FUSION)
                      | (0 if overlap else _capi.FLAG_NO_OVERLAP) | (0 if pml_split else _capi.FLAG_NO_PML_SPLIT)
-                     | (0 if temporal else _capi.FLAG_NO_TEMPORAL))
+                     | (0 if temporal else _capi.FLAG_NO_TEMPORAL) | (_capi.FLAG_F32_ARITH if f32_arith else 0)
+                     | (_capi.FLAG_UNIFORM_SLABS if uniform_slabs else 0))
         cfg.pml_mode = _pml_mode
         cfg.pml_percent = float(_pml_percent)
         for a in range(3):

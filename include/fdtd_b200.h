@@ -76,6 +76,11 @@ typedef enum fdtd_status {
 #define FDTD_FLAG_NO_OVERLAP 0x8u     /* multi-GPU: issue the halo exchange on the compute stream (no overlap) */
 #define FDTD_FLAG_NO_PML_SPLIT 0x10u  /* PML: one launch per sweep with a per-cell predicate instead of interior + shell launches */
 #define FDTD_FLAG_NO_TEMPORAL 0x20u   /* fdtd_step(n): never pair steps into the temporally blocked two-step pass */
+#define FDTD_FLAG_F32_ARITH 0x80u     /* FDTD_F32 only, opt-in, NOT a reference mode: float storage AND float arithmetic (every operation
+                                         rounded to float, same association, no FMA contraction; 4 cells per lane).  The default FDTD_F32 mode
+                                         (float storage, double arithmetic) is what a float build of the reference computes;
+                                         this one trades bits for speed and is validated against the fp64 reference at north_star's fp32
+                                         tolerance (<= 1e-5 relative L-inf) and bit for bit against the oracle's float-arithmetic restatement. */
 #define FDTD_FLAG_UNIFORM_SLABS 0x40u /* multi-GPU PML: equal slab heights instead of cost-weighted ones (fdtd_slab_range_cfg) */
 
 typedef enum fdtd_pml_mode {
@@ -115,6 +120,8 @@ typedef struct fdtd_info {
     int32_t transport;         /* halo transport of a multi-rank solver: 0 none (single GPU / not initialised), 1 NCCL send/recv,
                                   2 copy engines into peer-mapped ghost planes (CUDA IPC or in-process peer access) */
     int32_t halo_in_kernel;    /* 1: the two-step pass waits for the halo inside the kernel (one launch per pass per rank) */
+    int32_t f32_arith;         /* 1: FDTD_FLAG_F32_ARITH in effect */
+    int32_t reserved0;
 } fdtd_info_t;
 
 /* ---- life cycle --------------------------------------------------------- */

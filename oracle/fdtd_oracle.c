@@ -92,6 +92,7 @@ DECL_TYPED(oracle_f32_t, float)
 /* float storage AND float arithmetic (the GPU library's opt-in FDTD_FLAG_F32_ARITH mode; is_f32 == 2) */
 #define REAL float
 #define ARITH float
+#define ARITH_FMA 1
 #define SUFFIX _f32a
 #define oracle_t oracle_f32_t
 #include "fdtd_oracle_body.inc"

@@ -582,3 +582,48 @@ def test_golden_kokkos_distinct_currents(golden_dir):
             for c, nm in enumerate(["EX", "EY", "EZ", "BX", "BY", "BZ"]):
                 assert np.array_equal(g.download(c), z[f"{nm}_step{s}"]), f"{nm} step {s} fusion={fusion}"
         g.close()
+
+
+# ---- opt-in fp32 arithmetic (FDTD_FLAG_F32_ARITH): float storage AND float arithmetic, 4 cells per lane ---------------
+@pytest.mark.parametrize("shape,steps,pml", [((16, 12, 10), 7, None), ((64, 64, 64), 5, None), ((128, 48, 12), 6, None), ((252, 30, 7), 4, None),
+                                             ((256, 64, 6), 5, None), ((120, 9, 6), 3, None), ((36, 8, 4), 9, None),
+                                             ((64, 48, 48), 6, 0.1), ((20, 16, 12), 5, 0.2)])
+def test_f32_arith_mode_bit_exact_vs_float_oracle(shape, steps, pml):
+    """Every kernel family of the mode (T2 pass with 128-cell TMA boxes, the two sweeps for single steps and the deferred
+    half step, the PML rim sweeps) against the oracle's float-arithmetic restatement (same association, every operation
+    rounded to float, no contraction): bit for bit, distinct Jx / Jy / Jz."""
+    Ni, Nj, Nk = shape
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), dtype=np.float32, pml=pml, f32_arith=True)
+    assert g.info().f32_arith == 1
+    load_both(o, g, seeded_fields(71, (Nk, Nj, Ni), dtype=np.float32, same_j=False))
+    o.step(steps); g.step(steps)
+    assert_bit_equal(o, g, what=f"f32 arithmetic {shape} pml={pml}")
+    for _ in range(3):
+        o.update_fields(); g.update_fields()
+    assert_bit_equal(o, g, what=f"f32 arithmetic {shape}, update_fields loop")
+    if pml is None and Ni % 4 == 0 and Nk >= 4:
+        assert g.info().passes_t2 == steps // 2 + 1
+
+
+@pytest.mark.parametrize("steps", [100, 1000])
+def test_f32_arith_mode_within_north_star_tolerance(steps):
+    """north_star's fp32 bar: <= 1e-5 relative L-inf against the fp64 reference semantics after N steps -- the sample
+    scenario (perf-tests/sample/sample.cpp: point source for 40 steps, then free propagation), 100 and 1000 steps."""
+    import math
+    n = 32
+    o = Oracle(**sample_params(n))
+    run_sample(o, n, steps)
+    g = fb.FDTD(params(n, n, n), 0.2, dtype=np.float32, f32_arith=True)
+    lo, hi, active, _ = sample_source(n, steps)
+    PI, T, Tx = 3.14159265358, 8.0, 4.0 * C
+    amp = [math.sin(2.0 * PI * (float(t + 1) * 0.2) / T) for t in range(active)]
+    w = [[math.pow(math.cos(2.0 * PI * (float(i) * C) / Tx), 2.0) for i in range(lo[a], hi[a])] for a in range(3)]
+    g.set_source(lo, hi, w[0], w[1], w[2], amp)
+    g.step(steps)
+    worst = max(rel_linf(g.download(c), o.field(c)) for c in range(6))
+    assert worst <= 1e-5, worst
+
+
+def test_f32_arith_needs_float_storage():
+    with pytest.raises(TypeError):
+        fb.FDTD(params(8, 8, 8), 0.2, dtype=np.float64, f32_arith=True)

@@ -24,7 +24,7 @@ def seeded_fields(seed, shape, dtype=np.float64, same_j=True):
 def make_pair(Ni, Nj, Nk, d=(C, C, C), dt=0.2, dtype=np.float64, pml=None, j_mode=J_KOKKOS, fusion=True,
               pml_thickness=None, **extra):
     """(oracle, gpu solver) on the same grid."""
-    o = Oracle(Ni, Nj, Nk, d[0], d[1], d[2], dt, dtype=dtype, j_mode=j_mode, pml_percent=pml)
+    o = Oracle(Ni, Nj, Nk, d[0], d[1], d[2], dt, dtype=dtype, j_mode=j_mode, pml_percent=pml, f32_arith=bool(extra.get("f32_arith", False)))
     p = params(Ni, Nj, Nk, *d)
     kw = dict(dtype=dtype, j_openmp_quirk=(j_mode == J_OPENMP), fusion=fusion, **extra)
     if pml is None and pml_thickness is None:
