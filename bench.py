@@ -347,7 +347,7 @@ def run_ours(a):
     # synthetic inputs in pinned host memory (also the e2e leg's H2D source)
     tdt = torch.float64 if a.dtype == "f64" else torch.float32
     host, pinned = [], True
-    for _ in range(6):
+    for _ in range(0 if a.zero_init else 6):
         t = torch.empty((nk_local, n, n), dtype=tdt)
         if pinned:
             try:
@@ -376,7 +376,7 @@ def run_ours(a):
         verify = verify_against_cpu(fb, n, dtype, local)
 
     # ---- device-resident leg: inputs already in HBM when the timed region starts --------------------------
-    for c in range(6):
+    for c in range(0 if a.zero_init else 6):
         g.upload(c, host[c].numpy())
     g.set_source(lo, hi, w[0], w[1], w[2], amp)
     g.step(a.warmup)
@@ -414,6 +414,8 @@ def run_ours(a):
     probe_idx = np.array([i + j * n + kmid * n * n for j in range(n // 2 - 5, n // 2 + 5) for i in range(n // 2 - 5, n // 2 + 5)],
                          dtype=np.int64)
     wprod = np.array([(w[0][(q % n) - lo[0]], w[1][((q // n) % n) - lo[1]], w[2][(q // (n * n)) - lo[2]]) for q in src_idx])
+    if a.zero_init:
+        a.no_e2e = True
     e2e_steps = a.steps
     amp = amp[-(e2e_steps + 1):]
     barrier()
@@ -503,7 +505,8 @@ def run_ours(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "reps": a.reps, "rep_ms": rep_ms, "timing": "median of `reps` blocks of `steps` steps, each block timed with CUDA events on the solver's stream "
                                                         "(max over ranks per block) and closed by fdtd_flush(): the trailing B half step is inside the timed region",
-            "scaling": a.scaling, "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "scaling": a.scaling, "vs_baseline": None, "dtype": a.dtype,
+            "data": "synthetic (zero initial fields + the sample source; no host arrays)" if a.zero_init else "synthetic",
             "config": workload_config(a, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -556,6 +559,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): n^3 per GPU; strong: n^3 in total, z-slabs of n/N planes (BASELINE configs[3])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (scaling probes)")
+    ap.add_argument("--zero-init", action="store_true", help="fields start at zero (plus the source): no host arrays, no uploads, no e2e leg "
+                                                             "(1024^3 on one GPU: 48 GiB of host fields are not worth generating for a timing run, SURVEY.md 8(d) C4)")
     ap.add_argument("--reps", type=int, default=None, help="timed blocks of --steps steps (default 5); the median block is reported")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the 4-step parity spot check against the CPU checker (N = 1)")
     ap.add_argument("--timeline", action="store_true", help="N > 1: record per-pass CUDA events on every rank -> gpurun_out/timeline_n<N>_rank<r>.json")

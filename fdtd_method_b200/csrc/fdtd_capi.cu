@@ -199,6 +199,7 @@ static void read_tunables(Tunables& t) {
     t.no_lazy = env_int("FDTD_B200_NO_LAZY", 0) != 0;
     t.mgpu_debug = env_int("FDTD_B200_MGPU_DEBUG", 0);
     t.pml_t2_f32 = env_int("FDTD_B200_PML_T2_F32", 0) != 0;
+    t.halo_timeout_s = std::max(1, env_int("FDTD_B200_HALO_TIMEOUT_S", 30));
 }
 // one cudaFuncSetAttribute per kernel family and solver (bit in Solver::configured)
 enum { CFG_FUSED2 = 0, CFG_T2 = 8 };
@@ -416,6 +417,7 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
         a.halo_flags = peer_data_flags(s);
         a.halo_err = peer_error_word(s);
         a.halo_seq = halo_seq;
+        a.halo_timeout_ns = (unsigned long long)s->tun.halo_timeout_s * 1000000000ull;
     }
     const int by = variant < 3 ? by_of_variant[variant] : 16;
     if (const CUtensorMap* tm = cached_tmaps(s, s->cur, by)) {

@@ -93,7 +93,8 @@ struct FusedT2Args {
     // neighbour) / halo_flags[1] (upper neighbour) to the exchange number.  A CTA whose chunk reads ghost planes waits
     // until the flag has reached halo_seq; z_rot issues those chunks last (chunk order 1, 2, ..., nz-1, 0).
     const unsigned* halo_flags;   // nullptr: nothing to wait for
-    unsigned* halo_err;           // set to 1 when a wait gives up (2 s): the host reports it at fdtd_sync
+    unsigned* halo_err;           // set to 1 when a wait gives up (halo_timeout_ns): the host reports it at fdtd_sync
+    unsigned long long halo_timeout_ns;   // generous (30 s by default): ranks may reach their first pass seconds apart
     unsigned halo_seq;
     int z_rot;
     alignas(64) CUtensorMap tmE[3];
@@ -284,14 +285,15 @@ __device__ __forceinline__ void t2_chunk_of(const FusedT2Args<T>& a, int& kb, in
 
 // Wait (one thread, then the CTA) until the neighbour's planes of exchange `seq` have landed in this rank's ghost
 // planes.  The flag is written by the neighbour's copy engine after its plane copies, on the same stream.
-__device__ __forceinline__ void t2_halo_wait(const unsigned* flag, unsigned seq, unsigned* err) {
+__device__ __forceinline__ void t2_halo_wait(const unsigned* flag, unsigned seq, unsigned* err, unsigned long long timeout_ns) {
     unsigned v;
-    long long t0 = 0;
+    unsigned long long t0 = 0, now;
     for (;;) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - seq) >= 0) break;
-        if (t0 == 0) t0 = clock64();
-        else if (clock64() - t0 > 4000000000LL) { *err = 1u; break; }   // ~2 s: a neighbour died; do not hang the GPU
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) { *err = 1u; break; }   // a neighbour died: give up rather than hang the GPU for ever
         __nanosleep(200);
     }
 }
@@ -644,8 +646,8 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
         const bool need_dn = kb - 2 < 0, need_up = ke + 1 >= a.g.nk;
         if (need_dn || need_up) {
             if (threadIdx.x == 0 && threadIdx.y == 0) {
-                if (need_dn) t2_halo_wait(a.halo_flags + 0, a.halo_seq, a.halo_err);
-                if (need_up) t2_halo_wait(a.halo_flags + 1, a.halo_seq, a.halo_err);
+                if (need_dn) t2_halo_wait(a.halo_flags + 0, a.halo_seq, a.halo_err, a.halo_timeout_ns);
+                if (need_up) t2_halo_wait(a.halo_flags + 1, a.halo_seq, a.halo_err, a.halo_timeout_ns);
             }
             __syncthreads();
             asm volatile("fence.proxy.async;" ::: "memory");   // the TMA loads of the ghost planes are ordered after the acquire

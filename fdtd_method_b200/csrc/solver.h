@@ -33,6 +33,7 @@ struct Tunables {
     bool no_lazy = false;     // FDTD_B200_NO_LAZY
     int mgpu_debug = 0;       // FDTD_B200_MGPU_DEBUG (timing experiments, tools/mgpu_probe.py)
     bool pml_t2_f32 = false;  // FDTD_B200_PML_T2_F32
+    int halo_timeout_s = 30;  // FDTD_B200_HALO_TIMEOUT_S: how long a pass CTA waits for a neighbour's planes before giving up
 };
 
 struct Solver {

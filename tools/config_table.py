@@ -19,10 +19,11 @@ import fdtd_method_b200 as fb  # noqa: E402
 from bench import C, sample_source_tables  # noqa: E402
 
 
-def run(name, n, dtype, steps, warmup=10, pml=None, random_init=True, source=True, reps=3):
+def run(name, n, dtype, steps, warmup=10, pml=None, random_init=True, source=True, reps=3, f32_arith=False):
     p = fb.Parameters(n, n, n, -n / 2 * C, n / 2 * C, -n / 2 * C, n / 2 * C, -n / 2 * C, n / 2 * C, C, C, C)
     npdt = np.float64 if dtype == "f64" else np.float32
-    g = fb.FDTD(p, 0.2, dtype=npdt) if pml is None else fb.FDTD_PML(p, 0.2, pml_thickness=(pml, pml, pml), dtype=npdt)
+    kw = dict(dtype=npdt, f32_arith=f32_arith)
+    g = fb.FDTD(p, 0.2, **kw) if pml is None else fb.FDTD_PML(p, 0.2, pml_thickness=(pml, pml, pml), **kw)
     if random_init:
         rng = np.random.default_rng(42)
         a = rng.uniform(-1, 1, size=(n, n, n)).astype(npdt)
@@ -38,6 +39,7 @@ def run(name, n, dtype, steps, warmup=10, pml=None, random_init=True, source=Tru
     for _ in range(reps):
         g.timer_start()
         g.step(steps)
+        g.flush()            # the closing B half step is inside the timed region
         ms.append(g.timer_stop() / steps)
     info = g.info()
     g.close()
@@ -63,7 +65,9 @@ if __name__ == "__main__":
     run("C2 256^3 f64 periodic", 256, "f64", 200 if q else 1000, source=False)
     run("C3 512^3 f64 source", 512, "f64", 50 if q else 200)
     run("C3 512^3 f32 source", 512, "f32", 50 if q else 200)
+    run("C3 512^3 f32 source, FDTD_FLAG_F32_ARITH (opt-in float arithmetic, not a reference mode)", 512, "f32", 50 if q else 200, f32_arith=True)
     run("C5/P=1 512^3 f64 PML 32", 512, "f64", 20 if q else 100, pml=32)
     run("C5/P=1 512^3 f32 PML 32", 512, "f32", 20 if q else 100, pml=32)
+    run("C5/P=1 512^3 f32 PML 32, FDTD_FLAG_F32_ARITH", 512, "f32", 20 if q else 100, pml=32, f32_arith=True)
     if not a.skip_1024:
         run("C4/P=1 1024^3 f64 periodic (zero init + source)", 1024, "f64", 10 if q else 40, warmup=4, random_init=False)

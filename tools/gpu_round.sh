@@ -74,9 +74,10 @@ kc)
     ncu_rows $out/kc_${n}_$kc.csv n=$n kc=$kc
   done | tee $out/kc_traffic.jsonl ;;
 mtests)
-  ( time timeout 1500 python -m pytest tests/test_multi_gpu.py -m gpu -q -rs ) > $out/pytest_mgpu_n$N.log 2>&1; tail -6 $out/pytest_mgpu_n$N.log | cut -c1-300 ;;
+  ( time timeout 1500 python -m pytest tests/test_multi_gpu.py -m gpu -q -rs -v ${MTESTS_K:+-k "$MTESTS_K"} ) > $out/pytest_mgpu_n$N.log 2>&1; tail -14 $out/pytest_mgpu_n$N.log | cut -c1-200 ;;
 mcoarray)   # the coarray-style program with $N images (cpp/coarray, f4) + the C++ multi-GPU class tests
-  ( timeout 600 python -m pytest tests/test_cpp_api_gpu.py -m gpu -q -rs ) > $out/pytest_cpp_n$N.log 2>&1; tail -4 $out/pytest_cpp_n$N.log | cut -c1-300 ;;
+  ( timeout 600 python -m pytest tests/test_cpp_api_gpu.py -m gpu -q -rs -v ) > $out/pytest_cpp_n$N.log 2>&1; tail -24 $out/pytest_cpp_n$N.log | cut -c1-200
+  ( timeout 300 cpp/bin/fdtd_coarray_b200 --images $N 64 64 $((32 * N)) 50 ) > $out/coarray_${N}_images.log 2>&1; head -8 $out/coarray_${N}_images.log ;;
 mbench)     # weak scaling (the driver's contract) with the per-pass timeline, same-box N = 1, PML weak, 1024^3 strong
   timeout 600 python bench.py --steps 200 --warmup 10 --reps 3 --no-cpu --no-e2e --no-verify > $out/bench_n1_samebox.json 2> $out/bench_n1_samebox.err; cut -c1-300 $out/bench_n1_samebox.json
   timeout 600 $TR --master-port 29521 bench.py --gpus $N --steps 200 --warmup 10 --reps 3 --no-e2e --timeline > $out/bench_n$N.json 2> $out/bench_n$N.err; cut -c1-300 $out/bench_n$N.json
@@ -85,6 +86,27 @@ mbench)     # weak scaling (the driver's contract) with the per-pass timeline, s
   timeout 600 $TR --master-port 29523 bench.py --gpus $N --steps 100 --warmup 10 --reps 3 --size 1024 --scaling strong --no-e2e > $out/bench_strong1024_n$N.json 2> $out/bench_strong1024_n$N.err; cut -c1-300 $out/bench_strong1024_n$N.json ;;
 mdriver)    # exactly what the driver runs at N > 1 (short window, e2e leg included)
   timeout 600 $TR --master-port 29531 bench.py --gpus $N --steps 20 --warmup 5 > $out/bench_n${N}_driver_args.json 2> $out/bench_n${N}_driver_args.err; cut -c1-300 $out/bench_n${N}_driver_args.json ;;
+m8)         # the one 8-GPU session of a round: same-box series at N = 1, 4, 8 for the three configurations + parity at 8 ranks
+  ( time timeout 600 python -m pytest "tests/test_multi_gpu.py::test_zslab_ring_bit_exact[8-peer-inkernel]" -m gpu -q -rs ) > $out/pytest_mgpu_n8.log 2>&1; tail -5 $out/pytest_mgpu_n8.log | cut -c1-200
+  B="--steps 200 --warmup 10 --reps 3 --no-e2e --no-cpu"
+  timeout 300 python bench.py $B --no-verify > $out/bench_n1.json 2> $out/bench_n1.err; cut -c1-200 $out/bench_n1.json
+  for n in 8 4; do
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2960$n bench.py --gpus $n $B --timeline > $out/bench_n$n.json 2> $out/bench_n$n.err; cut -c1-200 $out/bench_n$n.json
+    mkdir -p $out/timeline_n$n; mv gpurun_out/timeline_n${n}_rank*.json $out/timeline_n$n/ 2>/dev/null
+  done
+  FDTD_B200_TRANSPORT=nccl timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 8 $B --timeline > $out/bench_n8_nccl.json 2> $out/bench_n8_nccl.err; cut -c1-200 $out/bench_n8_nccl.json
+  mkdir -p $out/timeline_n8_nccl; mv gpurun_out/timeline_n8_rank*.json $out/timeline_n8_nccl/ 2>/dev/null
+  P="--steps 100 --warmup 10 --reps 3 --no-e2e --no-cpu --workload pml"
+  timeout 300 python bench.py $P > $out/bench_pml_n1.json 2> $out/bench_pml_n1.err; cut -c1-200 $out/bench_pml_n1.json
+  for n in 8 4; do
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2962$n bench.py --gpus $n $P > $out/bench_pml_n$n.json 2> $out/bench_pml_n$n.err; cut -c1-200 $out/bench_pml_n$n.json
+  done
+  S="--steps 60 --warmup 6 --reps 3 --no-e2e --no-cpu --no-verify --zero-init --size 1024 --scaling strong"
+  for n in 8 4; do
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2963$n bench.py --gpus $n $S > $out/bench_strong1024_n$n.json 2> $out/bench_strong1024_n$n.err; cut -c1-200 $out/bench_strong1024_n$n.json
+  done
+  timeout 500 python bench.py --steps 30 --warmup 4 --reps 3 --no-e2e --no-cpu --no-verify --zero-init --size 1024 --scaling strong > $out/bench_strong1024_n1.json 2> $out/bench_strong1024_n1.err; cut -c1-200 $out/bench_strong1024_n1.json
+  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29641 bench.py --gpus 8 --steps 20 --warmup 5 > $out/bench_n8_driver_args.json 2> $out/bench_n8_driver_args.err; cut -c1-200 $out/bench_n8_driver_args.json ;;
 mab)        # transports side by side: copy engines + halo wait in the kernel (default) / + three-stream boundary launches / NCCL
   FDTD_B200_HALO_IN_KERNEL=0 timeout 600 $TR --master-port 29524 bench.py --gpus $N --steps 200 --warmup 10 --reps 3 --no-e2e --timeline > $out/bench_n${N}_peer3stream.json 2> $out/bench_n${N}_peer3stream.err; cut -c1-300 $out/bench_n${N}_peer3stream.json
   mkdir -p $out/timeline_n${N}_peer3stream; mv gpurun_out/timeline_n${N}_rank*.json $out/timeline_n${N}_peer3stream/ 2>/dev/null
