@@ -400,6 +400,14 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     const A cBx = (A)a.c.cBx, cBy = (A)a.c.cBy, cBz = (A)a.c.cBz;
     const A cEx = (A)a.c.cEx, cEy = (A)a.c.cEy, cEz = (A)a.c.cEz, cJ = (A)a.c.cJ;
 
+    // Halo hand-off, upper side: this iteration issues the ring fill of plane k + 2, which reads E(k + 3) -- from k = nk - 3
+    // on, the upper neighbour's ghost planes.  The CTA waits here, at the last possible moment (the top chunk only needs
+    // them in its last iterations), not when it starts.  Block-uniform condition on kernel parameters and c.ke.
+    if (a.halo_flags != nullptr && k == a.g.nk - 3 && c.ke >= a.g.nk - 1) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) t2_halo_wait(a.halo_flags + 1, a.halo_seq, a.halo_err, a.halo_timeout_ns);
+        __syncthreads();
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
     // ================= phase X: B1(k) =============================================================================
     if (TMA) {
         extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -642,13 +650,11 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     t2_chunk_of(a, kb, ke);
     const int k0 = a.g.k0 + kb - 2, k1 = a.g.k0 + ke + 1;
     if (a.halo_flags) {
-        // the chunk reads planes kb-2 .. ke+1: ghost planes below 0 come from the lower neighbour, at or above nk from the upper
-        const bool need_dn = kb - 2 < 0, need_up = ke + 1 >= a.g.nk;
-        if (need_dn || need_up) {
-            if (threadIdx.x == 0 && threadIdx.y == 0) {
-                if (need_dn) t2_halo_wait(a.halo_flags + 0, a.halo_seq, a.halo_err, a.halo_timeout_ns);
-                if (need_up) t2_halo_wait(a.halo_flags + 1, a.halo_seq, a.halo_err, a.halo_timeout_ns);
-            }
+        // the chunk reads planes kb-2 .. ke+1: ghost planes below 0 come from the lower neighbour and are needed at once
+        // (the bottom chunk is issued last); planes at or above nk come from the upper neighbour and are needed by the last
+        // iterations of the top chunk only -- that wait sits in the plane loop (t2_plane)
+        if (kb - 2 < 0) {
+            if (threadIdx.x == 0 && threadIdx.y == 0) t2_halo_wait(a.halo_flags + 0, a.halo_seq, a.halo_err, a.halo_timeout_ns);
             __syncthreads();
             asm volatile("fence.proxy.async;" ::: "memory");   // the TMA loads of the ghost planes are ordered after the acquire
         }

@@ -11,6 +11,7 @@
 #   launches     ncu launch list (gpu__time_duration.sum) of the bench command
 #   ncu          ncu --set full of the T2 pass, fp64 and fp32
 #   pml          PML launch list with DRAM bytes + ncu --set full of the sweeps + PML bench line
+#   sanitize     compute-sanitizer memcheck / racecheck / synccheck over tools/sanitize_driver.py
 #   e2e          tools/e2e_breakdown.py
 #   kc           DRAM traffic / duration of the T2 pass vs chunk length (512^3 and 1024^3)
 # N-GPU stages (set NGPU=2|4|8 and call gpurun --gpus $NGPU)
@@ -64,6 +65,11 @@ pml)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:sweep_ -s 12 -c 4 -f -o $out/pml_full \
       python bench.py --workload pml --steps 4 --warmup 3 --no-cpu --no-e2e > $out/ncu_pml_full.log 2>&1
   timeout 600 python bench.py --workload pml --steps 100 --warmup 10 --no-cpu > $out/bench_pml.json 2> $out/bench_pml.err; cut -c1-300 $out/bench_pml.json ;;
+sanitize)   # compute-sanitizer memcheck + racecheck (shared-memory hazards of the single-buffered row exchanges) + synccheck
+  for tool in memcheck racecheck synccheck; do
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_driver.py > $out/sanitizer_$tool.log 2>&1
+    grep -E "ERROR SUMMARY|RACECHECK SUMMARY|all cases|Error|hazard" $out/sanitizer_$tool.log | head -8
+  done ;;
 e2e)
   timeout 300 python tools/e2e_breakdown.py --steps 60 > $out/e2e_breakdown.json 2> $out/e2e_breakdown.err; cat $out/e2e_breakdown.json ;;
 kc)
