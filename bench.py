@@ -299,7 +299,7 @@ def workload_config(a, world, note=None):
     strong = getattr(a, "scaling", "weak") == "strong"
     cfg = {"workload": f"{a.n}^3 {a.dtype} Yee grid {'in total (z-slabs of n/N planes, BASELINE configs[3])' if strong else 'per GPU'}, {'periodic' if a.workload == 'periodic' else 'PML 32 cells (pml_percent 0.0625 in i/j, explicit thickness)'}"
                        f", random E/B seed 42 + sample.cpp point current source active every step (BASELINE configs[2])",
-           "grid": [a.n, a.n, a.n * world if getattr(a, "scaling", "weak") == "weak" else a.n], "decomposition": f"z-slab x{world}" if world > 1 else "single GPU",
+           "grid": [a.n, a.n, a.n * world if getattr(a, "scaling", "weak") == "weak" else (getattr(a, "planes", 0) or a.n)], "decomposition": f"z-slab x{world}" if world > 1 else "single GPU",
            "dx=dy=dz": "C", "dt": 0.2, "l2": "working set 12+ GiB per GPU >> 126 MB L2 (no flush needed)"}
     if note:
         cfg["note"] = note
@@ -326,7 +326,7 @@ def run_ours(a):
     n = a.n
     dtype = np.float64 if a.dtype == "f64" else np.float32
     W = 8 if a.dtype == "f64" else 4
-    Nk = n * world if a.scaling == "weak" else n
+    Nk = n * world if a.scaling == "weak" else (a.planes or n)
     p = fb.Parameters(n, n, Nk, -n / 2 * C, n / 2 * C, -n / 2 * C, n / 2 * C, -Nk / 2 * C, Nk / 2 * C, C, C, C)
     kw = dict(dtype=dtype, device=local, rank=rank, nranks=world)
     if a.workload == "pml":
@@ -559,6 +559,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): n^3 per GPU; strong: n^3 in total, z-slabs of n/N planes (BASELINE configs[3])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (scaling probes)")
+    ap.add_argument("--planes", type=int, default=0, help="strong scaling: total number of k planes (default n); e.g. --size 1024 --planes 256 "
+                                                          "--gpus 2 gives every rank the 128-plane slab of the 1024^3 / 8-GPU configuration")
     ap.add_argument("--zero-init", action="store_true", help="fields start at zero (plus the source): no host arrays, no uploads, no e2e leg "
                                                              "(1024^3 on one GPU: 48 GiB of host fields are not worth generating for a timing run, SURVEY.md 8(d) C4)")
     ap.add_argument("--reps", type=int, default=None, help="timed blocks of --steps steps (default 5); the median block is reported")

@@ -283,8 +283,10 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
 
 // ---- temporally blocked pass: two Yee steps per launch (fused_kernel_t2.cuh) -------------------------------
 // Variant table <BY rows per CTA, min CTAs/SM>; FDTD_B200_T2_VARIANT picks one.
+struct T2Ranges { int lo, hi, lo2, hi2; };   // local plane ranges a T2 launch produces (second range empty when lo2 == hi2)
+
 template <typename T, typename A, int BY, int MINB, int ABL = 0>
-static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, int cfg_bit) {
+static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, const T2Ranges& rg, int cfg_bit) {
     constexpr int V = t2_v<A>();   // cells per lane: 2 with double arithmetic (both storage types), 4 with float arithmetic
     constexpr int TIU = FUSED_OUT_LANES * V;
     constexpr int TJU = BY - 4;
@@ -297,7 +299,22 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, int cfg_bit) 
     }
     const int gx = (s->g.Ni + TIU - 1) / TIU;
     const int gy = (s->g.Nj + TJU - 1) / TJU;
-    const int np = a.k_hi - a.k_lo, np2 = a.k_hi2 - a.k_lo2;
+    // Halo wait inside the kernel (one range = the rank's whole slab, possibly clipped by a PML store box): the planes that
+    // read ghost planes are split off as thin chunks (H output planes each, the pass's reach) and issued LAST, after all
+    // interior chunks -- by then the neighbours' pushes have long landed, and their short CTAs fill the interior's tail wave.
+    // (A first version kept full-length boundary chunks and lost 11 % in the strong-scaling regime -- 1024^2 planes, two
+    // chunks of 64: the top chunk's first wave reached the ghost planes 0.13 ms into the pass, the halo took 0.41 ms,
+    // profiles/strong_probe_r02.md.)  Each extra chunk costs ~5 plane iterations per tile: 2 % at 512 planes.
+    const int H = 2;
+    int lo = rg.lo, hi = rg.hi;
+    bool thin_top = false, thin_bot = false;
+    if (a.halo_flags != nullptr && rg.hi2 <= rg.lo2 && hi - lo >= 4 * H + 8) {
+        thin_bot = lo - 2 < 0;
+        thin_top = hi + 1 >= s->g.nk;
+        if (thin_bot) lo += H;
+        if (thin_top) hi -= H;
+    }
+    const int np = hi - lo, np2 = rg.hi2 - rg.lo2;
     int kc = s->tun.fused_kc;
     if (kc <= 0) {
         // Chunk count m of the (first) plane range: every chunk costs 3 redundant plane iterations plus ~2 of start-up,
@@ -326,9 +343,13 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, int cfg_bit) 
         kc = (np + best_m - 1) / best_m;
     }
     if (kc > np) kc = np;
-    a.kc = kc;
-    a.nz1 = (np + kc - 1) / kc;
-    const int gz = a.nz1 + (np2 + kc - 1) / kc;
+    while ((np + kc - 1) / kc + (np2 + kc - 1) / kc + 2 > T2_MAXCH) ++kc;
+    int gz = 0;
+    for (int k = lo; k < hi; k += kc) { a.chunk_lo[gz] = k; a.chunk_hi[gz] = std::min(k + kc, hi); ++gz; }
+    for (int k = rg.lo2; k < rg.hi2; k += kc) { a.chunk_lo[gz] = k; a.chunk_hi[gz] = std::min(k + kc, rg.hi2); ++gz; }
+    if (thin_top) { a.chunk_lo[gz] = hi; a.chunk_hi[gz] = rg.hi; ++gz; }
+    if (thin_bot) { a.chunk_lo[gz] = rg.lo; a.chunk_hi[gz] = lo; ++gz; }
+    a.nchunks = gz;
     a.gx = gx; a.gy = gy;
     {
         // tile columns per strip; >= gx = row-major ids: measured best (profiles/strip_r01.jsonl) -- a missed x-neighbour
@@ -336,9 +357,6 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, int cfg_bit) 
         const int w = s->tun.t2_strip > 0 ? s->tun.t2_strip : gx;
         a.strip_w = w > gx ? gx : w;
     }
-    // Halo-dependent chunks last: with the chunk order 1, 2, ..., nz-1, 0 the CTAs that read ghost planes (top chunk at
-    // its end, bottom chunk at its start) are dispatched after the interior ones, when the pushed planes have long landed.
-    a.z_rot = (a.halo_flags != nullptr && np2 == 0 && a.nz1 > 1) ? 1 : 0;
     if (a.n_half == 2) fused_BE_T2_kernel<T, A, BY, MINB, true, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
     else fused_BE_T2_kernel<T, A, BY, MINB, false, ABL><<<dim3(gx * gy, 1, gz), dim3(FUSED_BX, BY), smem, s->launch_stream>>>(a);
     return cudaGetLastError();
@@ -405,7 +423,8 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
         a.J[c] = static_cast<const T*>(s->p[JX + c][0]);
         a.s_lo[c] = s->src_lo[c]; a.s_hi[c] = s->src_hi[c]; a.sw[c] = s->d_w[c];
     }
-    a.k_lo = k_lo; a.k_hi = k_hi; a.k_lo2 = k_lo2; a.k_hi2 = k_hi2; a.n_half = n_half;
+    const T2Ranges rg{k_lo, k_hi, k_lo2, k_hi2};
+    a.n_half = n_half;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     a.src2 = src2; a.amp2 = amp2;
     for (int d = 0; d < 2; ++d) {
@@ -427,14 +446,14 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
     cudaError_t e;
     switch (variant) {
         default:
-        case 0: e = launch_t2_variant<T, A, 16, 1>(s, a, CFG_T2 + 0 + (sizeof(A) == 4 ? 8 : 0)); break;
-        case 1: e = launch_t2_variant<T, A, 8, 2>(s, a, CFG_T2 + 1 + (sizeof(A) == 4 ? 8 : 0)); break;
-        case 2: e = launch_t2_variant<T, A, 12, 1>(s, a, CFG_T2 + 2 + (sizeof(A) == 4 ? 8 : 0)); break;
+        case 0: e = launch_t2_variant<T, A, 16, 1>(s, a, rg, CFG_T2 + 0 + (sizeof(A) == 4 ? 8 : 0)); break;
+        case 1: e = launch_t2_variant<T, A, 8, 2>(s, a, rg, CFG_T2 + 1 + (sizeof(A) == 4 ? 8 : 0)); break;
+        case 2: e = launch_t2_variant<T, A, 12, 1>(s, a, rg, CFG_T2 + 2 + (sizeof(A) == 4 ? 8 : 0)); break;
 #ifdef FDTD_T2_ABLATE   /* timing experiments only: results are wrong */
-        case 11: e = launch_t2_variant<T, A, 16, 1, 1>(s, a, CFG_T2 + 3); break;
-        case 12: e = launch_t2_variant<T, A, 16, 1, 2>(s, a, CFG_T2 + 4); break;
-        case 13: e = launch_t2_variant<T, A, 16, 1, 3>(s, a, CFG_T2 + 5); break;
-        case 14: e = launch_t2_variant<T, A, 16, 1, 4>(s, a, CFG_T2 + 6); break;
+        case 11: e = launch_t2_variant<T, A, 16, 1, 1>(s, a, rg, CFG_T2 + 3); break;
+        case 12: e = launch_t2_variant<T, A, 16, 1, 2>(s, a, rg, CFG_T2 + 4); break;
+        case 13: e = launch_t2_variant<T, A, 16, 1, 3>(s, a, rg, CFG_T2 + 5); break;
+        case 14: e = launch_t2_variant<T, A, 16, 1, 4>(s, a, rg, CFG_T2 + 6); break;
 #endif
     }
     if (e != cudaSuccess) return cuda_fail(e, "fused_BE_T2_kernel launch");

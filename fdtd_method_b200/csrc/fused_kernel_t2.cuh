@@ -52,6 +52,8 @@
 
 namespace fdtd_b200 {
 
+constexpr int T2_MAXCH = 72;   // plane chunks per launch (1024 planes / 16 + the two thin boundary chunks, with room)
+
 template <typename T>
 struct FusedT2Args {
     Geom g;
@@ -62,9 +64,10 @@ struct FusedT2Args {
     T* Eout[3];
     T* Bout[3];
     JBox jbox;
-    int k_lo, k_hi;   // local planes [k_lo, k_hi) produced by this launch ...
-    int k_lo2, k_hi2; // ... plus a second range (the other boundary slab of a z-slab rank; empty otherwise)
-    int nz1;          // blockIdx.z < nz1 serves the first range
+    // Plane chunks: CTA (tile, z) produces local planes [chunk_lo[z], chunk_hi[z]).  The host builds the list (interior
+    // chunks first; on a slab rank whose kernel waits for the halo itself, a thin top and a thin bottom chunk last).
+    int nchunks;
+    int chunk_lo[T2_MAXCH], chunk_hi[T2_MAXCH];
     // Tile rasterisation: blockIdx.x is a linear tile id that walks strips of strip_w tile columns, row-major inside a
     // strip (strip_w = gx, the default: plain row-major).  CTAs are dispatched in id order, one at a time as SMs free
     // up, so the start-time skew between two tiles is about (chunk duration) x (id distance) / (CTAs in flight), and a
@@ -72,7 +75,6 @@ struct FusedT2Args {
     // the 16 rows a tile reads, x-neighbours the two 128-byte lines at the ends of every 512-byte row (640 / 480).
     // Narrow strips were measured and lost (profiles/strip_r01.jsonl); the host bounds the chunk length instead.
     int gx, gy, strip_w;
-    int kc;           // planes per CTA chunk
     int n_half;       // stage A: 1 or 2 half steps of B (stage B always applies 2)
     int j_quirk;      // Jx feeds all three components (FDTD_openmp semantics)
     // device-resident source evaluated in-kernel for stage B
@@ -91,12 +93,11 @@ struct FusedT2Args {
     // Halo hand-off inside the kernel (z-slab rank on the peer transport, csrc/peer_ring.cu): the neighbours' copy engines
     // push their boundary planes into this rank's ghost planes while the pass runs and then set halo_flags[0] (lower
     // neighbour) / halo_flags[1] (upper neighbour) to the exchange number.  A CTA whose chunk reads ghost planes waits
-    // until the flag has reached halo_seq; z_rot issues those chunks last (chunk order 1, 2, ..., nz-1, 0).
+    // until the flag has reached halo_seq before it starts; the host puts those (thin) chunks at the end of the list.
     const unsigned* halo_flags;   // nullptr: nothing to wait for
     unsigned* halo_err;           // set to 1 when a wait gives up (halo_timeout_ns): the host reports it at fdtd_sync
     unsigned long long halo_timeout_ns;   // generous (30 s by default): ranks may reach their first pass seconds apart
     unsigned halo_seq;
-    int z_rot;
     alignas(64) CUtensorMap tmE[3];
     alignas(64) CUtensorMap tmB[3];
 };
@@ -273,14 +274,11 @@ __device__ __forceinline__ void t2_update_E(A (&e)[3][V], const A (&b)[3][V], co
     }
 }
 
-// Plane chunk [kb, ke) of this CTA: blockIdx.z walks the chunks of the first plane range, then those of the second.
+// Plane chunk [kb, ke) of this CTA.
 template <typename T>
 __device__ __forceinline__ void t2_chunk_of(const FusedT2Args<T>& a, int& kb, int& ke) {
-    int z = (int)blockIdx.z;
-    const bool second = z >= a.nz1;
-    if (a.z_rot && !second) { z += 1; if (z == a.nz1) z = 0; }
-    kb = (second ? a.k_lo2 : a.k_lo) + (z - (second ? a.nz1 : 0)) * a.kc;
-    ke = min(kb + a.kc, second ? a.k_hi2 : a.k_hi);
+    kb = a.chunk_lo[blockIdx.z];
+    ke = a.chunk_hi[blockIdx.z];
 }
 
 // Wait (one thread, then the CTA) until the neighbour's planes of exchange `seq` have landed in this rank's ghost
@@ -400,14 +398,6 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     const A cBx = (A)a.c.cBx, cBy = (A)a.c.cBy, cBz = (A)a.c.cBz;
     const A cEx = (A)a.c.cEx, cEy = (A)a.c.cEy, cEz = (A)a.c.cEz, cJ = (A)a.c.cJ;
 
-    // Halo hand-off, upper side: this iteration issues the ring fill of plane k + 2, which reads E(k + 3) -- from k = nk - 3
-    // on, the upper neighbour's ghost planes.  The CTA waits here, at the last possible moment (the top chunk only needs
-    // them in its last iterations), not when it starts.  Block-uniform condition on kernel parameters and c.ke.
-    if (a.halo_flags != nullptr && k == a.g.nk - 3 && c.ke >= a.g.nk - 1) {
-        if (threadIdx.x == 0 && threadIdx.y == 0) t2_halo_wait(a.halo_flags + 1, a.halo_seq, a.halo_err, a.halo_timeout_ns);
-        __syncthreads();
-        asm volatile("fence.proxy.async;" ::: "memory");
-    }
     // ================= phase X: B1(k) =============================================================================
     if (TMA) {
         extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -650,11 +640,13 @@ __global__ void __launch_bounds__(FUSED_BX * BY, MINB) fused_BE_T2_kernel(const 
     t2_chunk_of(a, kb, ke);
     const int k0 = a.g.k0 + kb - 2, k1 = a.g.k0 + ke + 1;
     if (a.halo_flags) {
-        // the chunk reads planes kb-2 .. ke+1: ghost planes below 0 come from the lower neighbour and are needed at once
-        // (the bottom chunk is issued last); planes at or above nk come from the upper neighbour and are needed by the last
-        // iterations of the top chunk only -- that wait sits in the plane loop (t2_plane)
-        if (kb - 2 < 0) {
-            if (threadIdx.x == 0 && threadIdx.y == 0) t2_halo_wait(a.halo_flags + 0, a.halo_seq, a.halo_err, a.halo_timeout_ns);
+        // the chunk reads planes kb-2 .. ke+1: ghost planes below 0 come from the lower neighbour, at or above nk from the upper
+        const bool need_dn = kb - 2 < 0, need_up = ke + 1 >= a.g.nk;
+        if (need_dn || need_up) {
+            if (threadIdx.x == 0 && threadIdx.y == 0) {
+                if (need_dn) t2_halo_wait(a.halo_flags + 0, a.halo_seq, a.halo_err, a.halo_timeout_ns);
+                if (need_up) t2_halo_wait(a.halo_flags + 1, a.halo_seq, a.halo_err, a.halo_timeout_ns);
+            }
             __syncthreads();
             asm volatile("fence.proxy.async;" ::: "memory");   // the TMA loads of the ghost planes are ordered after the acquire
         }
