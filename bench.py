@@ -328,7 +328,7 @@ def run_ours(a):
     W = 8 if a.dtype == "f64" else 4
     Nk = n * world if a.scaling == "weak" else (a.planes or n)
     p = fb.Parameters(n, n, Nk, -n / 2 * C, n / 2 * C, -n / 2 * C, n / 2 * C, -Nk / 2 * C, Nk / 2 * C, C, C, C)
-    kw = dict(dtype=dtype, device=local, rank=rank, nranks=world)
+    kw = dict(dtype=dtype, device=local, rank=rank, nranks=world, f32_arith=bool(a.f32_arith))
     if a.workload == "pml":
         g = fb.FDTD_PML(p, 0.2, pml_thickness=(32, 32, 32), **kw)
     else:
@@ -372,7 +372,7 @@ def run_ours(a):
     # ---- parity spot check at the bench shape (rank 0, N = 1): 4 steps of a 64-plane slab of this very workload against
     # the reference itself (oracle/_ref) or the C oracle, bit for bit, BEFORE anything is timed ---------------------------
     verify = None
-    if a.verify and world == 1 and a.workload == "periodic":
+    if a.verify and world == 1 and a.workload == "periodic" and not a.f32_arith:
         verify = verify_against_cpu(fb, n, dtype, local)
 
     # ---- device-resident leg: inputs already in HBM when the timed region starts --------------------------
@@ -487,7 +487,7 @@ def run_ours(a):
             kernel = ("fused_BE_T2_kernel (one launch = TWO Yee steps of this rank's slab)" if t2 else
                       "fused_BE_kernel (one launch = one Yee step of this rank's slab)" if fused
                       else "sweep_B_kernel + sweep_E_kernel (two launches = one Yee step)")
-        traffic, traffic_src = ncu_traffic(a.dtype, n) if not pml else (None, None)
+        traffic, traffic_src = ncu_traffic("f32_arith" if a.f32_arith else a.dtype, n) if not pml else (None, None)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src,
@@ -505,7 +505,7 @@ def run_ours(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "reps": a.reps, "rep_ms": rep_ms, "timing": "median of `reps` blocks of `steps` steps, each block timed with CUDA events on the solver's stream "
                                                         "(max over ranks per block) and closed by fdtd_flush(): the trailing B half step is inside the timed region",
-            "scaling": a.scaling, "vs_baseline": None, "dtype": a.dtype,
+            "scaling": a.scaling, "vs_baseline": None, "dtype": a.dtype + ("_arith32 (opt-in FDTD_FLAG_F32_ARITH, not a reference mode)" if a.f32_arith else ""),
             "data": "synthetic (zero initial fields + the sample source; no host arrays)" if a.zero_init else "synthetic",
             "config": workload_config(a, world),
             "clocks": clocks,
@@ -559,6 +559,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): n^3 per GPU; strong: n^3 in total, z-slabs of n/N planes (BASELINE configs[3])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (scaling probes)")
+    ap.add_argument("--f32-arith", action="store_true", help="with --dtype f32: the opt-in FDTD_FLAG_F32_ARITH mode (float storage AND float "
+                                                             "arithmetic; not a reference mode -- labelled in `dtype` and `config`)")
     ap.add_argument("--planes", type=int, default=0, help="strong scaling: total number of k planes (default n); e.g. --size 1024 --planes 256 "
                                                           "--gpus 2 gives every rank the 128-plane slab of the 1024^3 / 8-GPU configuration")
     ap.add_argument("--zero-init", action="store_true", help="fields start at zero (plus the source): no host arrays, no uploads, no e2e leg "

@@ -53,11 +53,12 @@ table)
   timeout 900 python tools/config_table.py > $out/config_table.jsonl 2> $out/config_table.err; cut -c1-220 $out/config_table.jsonl ;;
 launches)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
-      python bench.py --steps 20 --warmup 3 --no-cpu > $out/bench_under_ncu.log 2>&1 ;;
+      python bench.py --steps 20 --warmup 5 --reps 2 --no-cpu --no-verify > $out/bench_under_ncu.log 2>&1 ;;
 ncu)
-  for dt in f64 f32; do
+  for dt in f64 f32 f32a; do
+    extra=""; d=$dt; if [ $dt = f32a ]; then d=f32; extra="--f32-arith"; fi
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_BE_T2 -s 4 -c 1 -f -o $out/t2_${dt}_full \
-        python bench.py --dtype $dt --steps 12 --warmup 3 --no-cpu --no-e2e > $out/ncu_$dt.log 2>&1
+        python bench.py --dtype $d $extra --steps 12 --warmup 3 --reps 1 --no-cpu --no-e2e --no-verify > $out/ncu_$dt.log 2>&1
   done ;;
 pml)
   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file $out/launches_pml.csv \
