@@ -667,9 +667,9 @@ static cudaEvent_t tl_event(Solver* s, int which) {
 // range empty when lo2 == hi2; halo_seq != 0 = the kernel waits for exchange number halo_seq itself.
 //
 // (A) peer transport + T2 pass (the default on a ring): ONE launch over the whole slab.  The copy engines push the 26
-//     boundary planes into the neighbours' ghost planes while the pass runs; the chunks that read ghost planes are issued
-//     last (chunk order 1 .. nz-1, 0) and their CTAs wait on the sequence flags -- no boundary launch, no redundant plane
-//     iterations, no SM ever runs anything but the pass:
+//     boundary planes into the neighbours' ghost planes while the pass runs; the planes that read ghost planes form two
+//     thin chunks at the end of the chunk list and their CTAs wait on the sequence flags -- no boundary launch, no third
+//     stream, no SM ever runs anything but the pass:
 //        comm stream    : wait(previous work) -> ready handshake -> plane copies -> data flags -> ev_b
 //        compute stream : the pass (whole slab) -> wait(ev_b: our planes have left before the next pass overwrites them)
 // (B) NCCL transport, or a kernel that cannot wait: three streams.  The pass kernels own every SM (one 512-thread CTA holds
