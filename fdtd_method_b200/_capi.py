@@ -11,7 +11,7 @@ import os
 from .structures import Parameters
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libfdtd_b200.so")
+LIB_PATH = os.environ.get("FDTD_B200_LIB") or os.path.join(_PKG, "libfdtd_b200.so")   # (override: A/B builds, build.py)
 
 F64, F32 = 0, 1
 PML_NONE, PML_PERCENT, PML_THICKNESS = 0, 1, 2

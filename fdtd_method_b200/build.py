@@ -8,7 +8,8 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libfdtd_b200.so")
+# FDTD_B200_LIB: build / load an alternative binary (A/B experiments with build-time switches), default the in-tree one
+LIB = os.environ.get("FDTD_B200_LIB") or os.path.join(PKG, "libfdtd_b200.so")
 SOURCES = ["fdtd_capi.cu", "nccl_ring.cu", "peer_ring.cu"]
 HEADERS = ["fdtd_common.cuh", "sweep_kernels.cuh", "fused_kernel.cuh", "fused_kernel_v2.cuh", "fused_kernel_t2.cuh", "solver.h", os.path.join("..", "..", "include", "fdtd_b200.h")]
 
@@ -19,7 +20,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
 ] + (["-DFDTD_T2_ABLATE"] if os.environ.get("FDTD_T2_ABLATE") else []) \
-  + (["-DFDTD_T2_F32_MAGIC=" + os.environ["FDTD_T2_F32_MAGIC"]] if os.environ.get("FDTD_T2_F32_MAGIC") else [])
+  + (["-DFDTD_T2_F32_MAGIC=" + os.environ["FDTD_T2_F32_MAGIC"]] if os.environ.get("FDTD_T2_F32_MAGIC") else []) \
+  + (["-DFDTD_T2_RINGUP=" + os.environ["FDTD_T2_RINGUP"]] if os.environ.get("FDTD_T2_RINGUP") else [])
 
 
 def nvcc() -> str:

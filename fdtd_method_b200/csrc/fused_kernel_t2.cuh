@@ -214,6 +214,14 @@ template <bool CS> __device__ __forceinline__ void t2_stg(float* p, const float 
 // by the adder (ties to even: M / ulp is even) and subtracting M is exact.  Float denormals: E clamped to -126.  Anything
 // at or above 2^127 (overflow to inf, NaN) takes the conversion path.  Two DADD + a few integer ops on the high word
 // instead of two F2F (which run at 16 per clock per SM).
+// FDTD_T2_RINGUP (build-time, default on; only where a lane's ring entry is 16 bytes of the arithmetic type, i.e. fp64 and
+// the fp32-arithmetic mode): stage A's "row above" values of old E(k) are read straight from the ring slot the TMA filled
+// for the previous plane (the row above is the next 512-byte ring row) instead of travelling through the E0 exchange rows:
+// two shared-memory stores fewer per thread and plane (of 22 accesses).  The refill of that slot moves behind barrier 1,
+// after everybody's reads of it.  The first plane of a chunk still takes the exchange rows (its old E came by plain loads).
+#ifndef FDTD_T2_RINGUP
+#define FDTD_T2_RINGUP 1
+#endif
 #ifndef FDTD_T2_F32_MAGIC
 #define FDTD_T2_F32_MAGIC 0   // build-time switch (fdtd_method_b200/build.py: FDTD_T2_F32_MAGIC=1 in the environment)
 #endif
@@ -394,6 +402,8 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     constexpr int NEXT = (SLOT + T2_D - 1) % T2_D;     // slot freed by the previous plane
     using IO = XIO<A>;
     using RIO = RingIO<T, A>;
+    constexpr bool RINGUP = FDTD_T2_RINGUP && sizeof(T) == sizeof(A) && ABL == 0;
+    constexpr int PREV = NEXT * SLOTB + t2_rrowb<T, A>();   // ring slot of the previous plane (old E(k), B0(k-1)), one row up
     const unsigned sa = c.sa, sr = c.sr;
     const A cBx = (A)a.c.cBx, cBy = (A)a.c.cBy, cBz = (A)a.c.cBz;
     const A cEx = (A)a.c.cEx, cEy = (A)a.c.cEy, cEz = (A)a.c.cEz, cJ = (A)a.c.cJ;
@@ -402,12 +412,14 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     if (TMA) {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
-        if (c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, A, BY, NEXT>(a, smem0, c.tile_x, c.tile_y, k + T2_D - 1);
+        if (!RINGUP && c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, A, BY, NEXT>(a, smem0, c.tile_x, c.tile_y, k + T2_D - 1);
         mbar_wait(smem0 + (unsigned)(t2_mbar0<T, A, BY>() + 8 * SLOT), parity);
-    } else {
+    } else if (!RINGUP) {
         if (k + T2_D - 1 <= c.ke && ABL != 3) t2_issue_slot<T, A, BY, NEXT>(a, c, k + T2_D - 1);
         cp_async_commit();
         cp_async_wait<T2_D - 1>();
+    } else {
+        cp_async_wait<T2_D - 2>();   // (the refill of slot NEXT is issued behind barrier 1: one group fewer in flight here)
     }
     RIO::template ld<RING + 1 * COMPB>(sr, en[1]);
     RIO::template ld<RING + 0 * COMPB>(sr, en[0]);
@@ -417,8 +429,13 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
         RIO::template ld<RING + 4 * COMPB>(sr, b[1]);
         RIO::template ld<RING + 5 * COMPB>(sr, b[2]);
         A ezu[V], exu[V];
-        IO::template ld<XE0z + UP>(sa, ezu);
-        IO::template ld<XE0x + UP>(sa, exu);
+        if (RINGUP && k != c.kb - 2) {
+            RIO::template ld<PREV + 2 * COMPB>(sr, ezu);
+            RIO::template ld<PREV + 0 * COMPB>(sr, exu);
+        } else {
+            IO::template ld<XE0z + UP>(sa, ezu);
+            IO::template ld<XE0x + UP>(sa, exu);
+        }
         const A ez_nl = __shfl_down_sync(FULL, e0[2][0], 1);
         const A ey_nl = __shfl_down_sync(FULL, e0[1][0], 1);
         if (ABL != 4) t2_update_B<T, A, V>(b, e0, en, ezu, exu, ez_nl, ey_nl, cBx, cBy, cBz, TWO_A);
@@ -428,8 +445,20 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
     if (ABL != 1) __syncthreads();   // barrier 1: B1(k) rows visible; everybody is done reading sE0 / sB2 of the previous plane
 
     // ================= phase Y: E1(k), then B2(k-1) ==================================================================
-    IO::template st<XE0z>(sa, en[2]);   // old E(k+1) rows for the next plane's phase X
-    IO::template st<XE0x>(sa, en[0]);
+    if (RINGUP) {
+        // everybody has read slot NEXT (own row in the previous plane, the row above in this one): refill it
+        if (TMA) {
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+            if (c.producer && k + T2_D - 1 <= c.ke) t2_issue_slot_tma<T, A, BY, NEXT>(a, smem0, c.tile_x, c.tile_y, k + T2_D - 1);
+        } else {
+            if (k + T2_D - 1 <= c.ke) t2_issue_slot<T, A, BY, NEXT>(a, c, k + T2_D - 1);
+            cp_async_commit();
+        }
+    } else {
+        IO::template st<XE0z>(sa, en[2]);   // old E(k+1) rows for the next plane's phase X
+        IO::template st<XE0x>(sa, en[0]);
+    }
     if (c.needE1) {
         A bzd[V], bxd[V], jv[3][V];
         IO::template ld<XB1z + DN>(sa, bzd);

@@ -126,3 +126,26 @@ def test_cost_weighted_slabs_for_pml():
     # no shell in k -> uniform; tiny grids -> uniform
     assert ranges(64, 64, 64, 4, _capi.PML_THICKNESS, (8, 8, 0)) == [fb.slab_range(64, r, 4) for r in range(4)]
     assert ranges(16, 16, 16, 4, _capi.PML_PERCENT, pct=0.2) == [fb.slab_range(16, r, 4) for r in range(4)]
+
+
+def test_cpp_callers_compile_against_the_headers():
+    """The drop-in C++ classes are header-only: every caller program under cpp/ (sample clone, kokkos_sample clone,
+    convergence unit tests, coarray-style program) must compile and link against the in-tree library without a GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None or shutil.which("make") is None:
+        pytest.skip("no g++ / make")
+    _capi.lib()   # builds libfdtd_b200.so if it is missing
+    r = subprocess.run(["make", "-B", "-C", os.path.join(ROOT, "cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    for exe in ("test_FDTD_method_b200", "sample_b200", "kokkos_sample_b200", "fdtd_coarray_b200"):
+        assert os.path.exists(os.path.join(ROOT, "cpp", "bin", exe)), exe
+    # without a GPU the programs fail loudly (no CPU fallback) instead of computing anything
+    r = subprocess.run([os.path.join(ROOT, "cpp", "bin", "sample_b200")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        assert r.returncode != 0 and "no CUDA device" in r.stdout, r.stdout[-500:]
