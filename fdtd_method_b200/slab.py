@@ -3,9 +3,11 @@
 The reference's only distributed design is the coarray program coarray/fdtd.F90: 1-D decomposition along
 z (:149-164), ring topology (:32-33), and per step two one-plane halo transfers -- Bx,By of the top owned
 plane to the next image (:90-91) and Ex,Ey of the bottom owned plane to the previous image (:97-98).
-Here the same ring runs over NCCL send/recv between B200s (csrc/nccl_ring.cu); this module holds the
-pieces that do not need a GPU: the plane ranges, the exchange plan, and the torch.distributed bootstrap
-that ships the NCCL unique id to every rank.
+Here the same ring runs between B200s over NVLink: by default every rank pushes its boundary planes into the neighbours'
+ghost planes with the copy engines (csrc/peer_ring.cu; the T2 pass waits for them inside the kernel), with NCCL
+send/recv (csrc/nccl_ring.cu) as bootstrap and fallback.  This module holds the pieces that do not need a GPU: the
+plane ranges, the exchange plan, and the torch.distributed bootstrap that ships the NCCL unique id to every rank.
+(One process driving several GPUs: fdtd_method_b200/multi.py.)
 """
 from __future__ import annotations
 
