@@ -427,6 +427,12 @@ static fdtd_status_t launch_t2(Solver* s, int n_half, int k_lo, int k_hi, int k_
     a.n_half = n_half;
     a.j_quirk = (s->cfg.flags & FDTD_FLAG_J_OPENMP_QUIRK) ? 1 : 0;
     a.src2 = src2; a.amp2 = amp2;
+    if (src2 == 2) {   // pending J writes: stage B takes J on the box from the dense buffers
+        for (int c = 0; c < 3; ++c) {
+            a.s_lo[c] = s->jp_lo[c]; a.s_hi[c] = s->jp_hi[c];
+            a.jb2[c] = static_cast<const T*>(s->d_jpend) + (size_t)c * Solver::JPEND_MAX_CELLS;
+        }
+    }
     for (int d = 0; d < 2; ++d) {
         a.sb_lo[d] = s->pml_t2 ? s->sb_lo[d] : 0;
         a.sb_hi[d] = s->pml_t2 ? s->sb_hi[d] : (d == 0 ? s->g.Ni : s->g.Nj);
@@ -655,6 +661,32 @@ static fdtd_status_t materialize_J(Solver* s) {
     return DISPATCH(s, launch_source, s, s->src_amp[s->src_t - 1], 0);
 }
 
+// ---- pending J writes (see Solver::jpend) ---------------------------------------------------------------------------
+template <typename T>
+static fdtd_status_t jbox_launch(Solver* s, int comp, int mode, const long long* d_idx, const T* d_vals, int n) {
+    JBoxArgs b;
+    for (int a = 0; a < 3; ++a) { b.lo[a] = s->jp_lo[a]; b.hi[a] = s->jp_hi[a]; }
+    T* box = static_cast<T*>(s->d_jpend) + (size_t)(comp - JX) * Solver::JPEND_MAX_CELLS;
+    const long long cells = (long long)(b.hi[0] - b.lo[0]) * (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
+    const int threads = 128;
+    const int blocks = (int)(((mode == 2 ? (long long)n : cells) + threads - 1) / threads);
+    jbox_kernel<T><<<blocks, threads, 0, s->stream>>>(static_cast<T*>(s->p[comp][0]), s->g, b, box, mode, d_idx, d_vals, n);
+    FDTD_CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    return FDTD_OK;
+}
+
+// Write the pending box into the J arrays (after the step that had to see the old J has been issued).
+static fdtd_status_t apply_pending_J(Solver* s) {
+    if (!s->jpend) return FDTD_OK;
+    s->jpend = false;
+    for (int c = JX; c <= JZ; ++c) {
+        fdtd_status_t st = (s->dtype == FDTD_F32) ? jbox_launch<float>(s, c, 1, nullptr, nullptr, 0) : jbox_launch<double>(s, c, 1, nullptr, nullptr, 0);
+        if (st != FDTD_OK) return st;
+    }
+    return FDTD_OK;
+}
+
 // ---- per-pass timeline (fdtd_timeline_enable): four timing events per overlapped pass -------------------------------
 //   [0] pass start (compute stream, before anything of the pass)      [1] halo copies start (after the ready handshake)
 //   [2] halo copies issued and done on this rank's side               [3] pass end (compute stream, kernels + halo)
@@ -778,9 +810,11 @@ static fdtd_status_t advance_pml_pair(Solver* s, int n_half, int src2, double am
     shrink_box(s, 1, V, lo, hi);
     if ((st = DISPATCH_A(s, launch_rim_sweep, s, false, 0, lo, hi, false)) != FDTD_OK) return st;
     if ((st = exchange_pair_planes(s, false, s->cur)) != FDTD_OK) return st;         // E1 bottom plane -> lower rank's plane nk
-    if (src2) {
+    if (src2 == 1) {
         // the rim may meet the source box: the second step's sweeps read J from the arrays
         if ((st = DISPATCH(s, launch_source, s, amp2, 0)) != FDTD_OK) return st;
+    } else if (src2 == 2) {
+        if ((st = apply_pending_J(s)) != FDTD_OK) return st;   // pending host writes: the arrays take them now (the T2 core read the box)
     }
     shrink_box(s, 0, 0, lo, hi);
     if ((st = DISPATCH_A(s, launch_rim_sweep, s, true, 2, lo, hi, true)) != FDTD_OK) return st;
@@ -811,11 +845,11 @@ static fdtd_status_t advance(Solver* s, int remaining, int* done) {
     const int n_half = s->b_pending ? 2 : 1;
     if (s->pml_t2 && remaining >= 2 && !s->tun.no_t2 &&
         !(s->src_active && s->src_t >= (int)s->src_amp.size())) {   // (the source does not retire between the two steps)
-        const int src2 = s->src_active ? 1 : 0;
-        const double amp2 = src2 ? s->src_amp[s->src_t] : 0.0;
+        const int src2 = s->src_active ? 1 : (s->jpend ? 2 : 0);
+        const double amp2 = src2 == 1 ? s->src_amp[s->src_t] : 0.0;
         st = advance_pml_pair(s, n_half, src2, amp2);
         if (st != FDTD_OK) return st;
-        if (src2) { s->src_t++; s->j_stale = false; }   // advance_pml_pair has written the second step's J
+        if (src2 == 1) { s->src_t++; s->j_stale = false; }   // advance_pml_pair has written the second step's J
         s->passes_t2++;
         *done = 2;
         s->cur ^= 1;
@@ -823,13 +857,13 @@ static fdtd_status_t advance(Solver* s, int remaining, int* done) {
         // Pair this step with the next one unless the source retires in between (J would have to change to zero).
         const bool src_ends = s->src_active && s->src_t >= (int)s->src_amp.size();
         if (s->t2 && remaining >= 2 && !src_ends && !s->tun.no_t2) {
-            const int src2 = s->src_active ? 1 : 0;
-            const double amp2 = src2 ? s->src_amp[s->src_t] : 0.0;
+            const int src2 = s->src_active ? 1 : (s->jpend ? 2 : 0);
+            const double amp2 = src2 == 1 ? s->src_amp[s->src_t] : 0.0;
             st = overlapped(s, s->ghosts_t2_valid, true,
                             [&](int lo, int hi, int lo2, int hi2, unsigned halo_seq) { return DISPATCH_A(s, launch_t2, s, n_half, lo, hi, lo2, hi2, src2, amp2, halo_seq); },
                             [&](cudaStream_t q, bool wait, cudaEvent_t e0, cudaEvent_t e1) { return exchange_t2(s, q, wait, e0, e1); });
             if (st != FDTD_OK) return st;
-            if (src2) { s->src_t++; s->j_stale = true; }
+            if (src2 == 1) { s->src_t++; s->j_stale = true; }
             s->passes_t2++;
             *done = 2;
         } else if (s->f32_arith) {
@@ -887,6 +921,7 @@ static void destroy_impl(Solver* s) {
         if (s->d_w[a]) cudaFree(s->d_w[a]);
     }
     if (s->d_stage) cudaFree(s->d_stage);
+    if (s->d_jpend) cudaFree(s->d_jpend);
     if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->ev_t0) cudaEventDestroy(s->ev_t0);
     if (s->ev_t1) cudaEventDestroy(s->ev_t1);
@@ -1068,6 +1103,9 @@ static fdtd_status_t run_steps(Solver* s, int nsteps) {
         st = advance(s, nsteps - t, &done);
         if (st != FDTD_OK) return st;
         t += done;
+        // pending J writes belong to the step after the first one issued here: either a two-step pass has just consumed the
+        // box in its second stage, or a single step has run on the old J -- in both cases the arrays take the writes now
+        if (s->jpend && (st = apply_pending_J(s)) != FDTD_OK) return st;
     }
     return materialize_J(s);
 }
@@ -1121,6 +1159,20 @@ static fdtd_status_t scatter_impl(Solver* s, int comp, const int64_t* idx, const
     FDTD_CUDA_TRY(cudaGetLastError());
     s->launches++;
     return FDTD_OK;
+}
+
+// fdtd_scatter of a J component into the pending box (Solver::jpend) instead of the array.
+template <typename T>
+static fdtd_status_t scatter_pending_impl(Solver* s, int comp, const int64_t* idx, const void* vals, size_t n) {
+    const size_t ib = round_up(n * sizeof(long long), 256), vb = n * sizeof(T);
+    fdtd_status_t st = ensure_stage(s, ib + vb);
+    if (st != FDTD_OK) return st;
+    FDTD_CUDA_TRY(cudaStreamSynchronize(s->stream));   // staging buffer may still be in flight
+    std::memcpy(s->h_stage, idx, n * sizeof(long long));
+    std::memcpy(static_cast<char*>(s->h_stage) + ib, vals, vb);
+    FDTD_CUDA_TRY(cudaMemcpyAsync(s->d_stage, s->h_stage, ib + vb, cudaMemcpyHostToDevice, s->stream));
+    return jbox_launch<T>(s, comp, 2, static_cast<const long long*>(s->d_stage),
+                          reinterpret_cast<const T*>(static_cast<char*>(s->d_stage) + ib), (int)n);
 }
 
 template <typename T>
@@ -1359,10 +1411,10 @@ fdtd_status_t fdtd_download(fdtd_solver_t* h, int comp, void* host, size_t count
 
 fdtd_status_t fdtd_scatter(fdtd_solver_t* h, int comp, const int64_t* idx, const void* values, size_t n) {
     Solver* s;
-    fdtd_status_t st = enter(h, &s);
+    fdtd_status_t st = check_handle(h, &s);
     if (st != FDTD_OK) return st;
     if ((st = check_component(comp)) != FDTD_OK) return st;
-    if (n == 0) return FDTD_OK;
+    if (n == 0) return flush_lazy(s);
     if (!idx || !values) return fail(FDTD_ERR_BAD_ARGUMENT, "null argument");
     const long long total = (long long)s->g.Ni * s->g.Nj * s->g.Nk, ij = (long long)s->g.Ni * s->g.Nj;
     int lo[3] = {s->g.Ni, s->g.Nj, s->g.Nk}, hi[3] = {0, 0, 0};
@@ -1372,6 +1424,27 @@ fdtd_status_t fdtd_scatter(fdtd_solver_t* h, int comp, const int64_t* idx, const
         const int c3[3] = {i, j, k};
         for (int a = 0; a < 3; ++a) { if (c3[a] < lo[a]) lo[a] = c3[a]; if (c3[a] + 1 > hi[a]) hi[a] = c3[a] + 1; }
     }
+    // J writes while one update_fields() call is recorded: keep them as a pending box so that the next call can still pair
+    // (a small box, no device source, every write inside the box the first of them opened)
+    if (comp >= JX && s->lazy_steps == 1 && !s->src_active && !s->tun.no_t2 && n <= (size_t)Solver::JPEND_MAX_CELLS) {
+        const long long vol = (long long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+        bool inside = s->jpend;
+        for (int a = 0; a < 3 && inside; ++a) inside = lo[a] >= s->jp_lo[a] && hi[a] <= s->jp_hi[a];
+        if (inside || (!s->jpend && vol <= Solver::JPEND_MAX_CELLS)) {
+            if (!s->jpend) {
+                if (!s->d_jpend) FDTD_CUDA_TRY(cudaMalloc(&s->d_jpend, (size_t)3 * Solver::JPEND_MAX_CELLS * s->esz));
+                for (int a = 0; a < 3; ++a) { s->jp_lo[a] = lo[a]; s->jp_hi[a] = hi[a]; }
+                for (int c = JX; c <= JZ; ++c) {   // the boxes start as copies of the arrays
+                    st = (s->dtype == FDTD_F32) ? jbox_launch<float>(s, c, 0, nullptr, nullptr, 0) : jbox_launch<double>(s, c, 0, nullptr, nullptr, 0);
+                    if (st != FDTD_OK) return st;
+                }
+                s->jpend = true;
+                jbox_union(s, lo, hi);   // J may be non-zero there from the next step on (a larger box only costs skipped skips)
+            }
+            return (s->dtype == FDTD_F32) ? scatter_pending_impl<float>(s, comp, idx, values, n) : scatter_pending_impl<double>(s, comp, idx, values, n);
+        }
+    }
+    if ((st = flush_lazy(s)) != FDTD_OK) return st;
     if (comp < JX) {
         if ((st = flush_pending(s)) != FDTD_OK) return st;
         invalidate_ghosts(s);

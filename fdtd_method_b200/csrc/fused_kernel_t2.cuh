@@ -79,6 +79,9 @@ struct FusedT2Args {
     int j_quirk;      // Jx feeds all three components (FDTD_openmp semantics)
     // device-resident source evaluated in-kernel for stage B
     int src2;                  // 1: cells inside [s_lo, s_hi) take J = ((amp2*wx)*wy)*wz in stage B
+                               // 2: cells inside [s_lo, s_hi) take J from the dense boxes jb2[] (host J writes issued between
+                               //    the two update_fields() calls this launch pairs, csrc/fdtd_capi.cu "pending J writes")
+    const T* jb2[3];           // mode 2: Jx, Jy, Jz on the box, [k][j][i] dense
     int s_lo[3], s_hi[3];      // global box
     const double* sw[3];       // device tables, indexed from s_lo
     double amp2;
@@ -517,7 +520,19 @@ __device__ __forceinline__ void t2_plane(const FusedT2Args<T>& a, const T2Ctx<T>
                 t2_ldg(a.J[0] + pj, jv[0]);
                 t2_ldg((a.j_quirk ? a.J[0] : a.J[1]) + pj, jv[1]);
                 t2_ldg((a.j_quirk ? a.J[0] : a.J[2]) + pj, jv[2]);
-                if (a.src2 && kgB >= a.s_lo[2] && kgB < a.s_hi[2] && c.jw >= a.s_lo[1] && c.jw < a.s_hi[1]) {
+                if (a.src2 == 2 && kgB >= a.s_lo[2] && kgB < a.s_hi[2] && c.jw >= a.s_lo[1] && c.jw < a.s_hi[1]) {
+                    const int bni = a.s_hi[0] - a.s_lo[0];
+                    const long long row = ((long long)(kgB - a.s_lo[2]) * (a.s_hi[1] - a.s_lo[1]) + (c.jw - a.s_lo[1])) * bni - a.s_lo[0];
+#pragma unroll
+                    for (int q = 0; q < V; ++q) {
+                        const int ii = c.i + q;
+                        if (ii >= a.s_lo[0] && ii < a.s_hi[0]) {
+                            jv[0][q] = (A)a.jb2[0][row + ii];
+                            jv[1][q] = (A)a.jb2[a.j_quirk ? 0 : 1][row + ii];
+                            jv[2][q] = (A)a.jb2[a.j_quirk ? 0 : 2][row + ii];
+                        }
+                    }
+                } else if (a.src2 == 1 && kgB >= a.s_lo[2] && kgB < a.s_hi[2] && c.jw >= a.s_lo[1] && c.jw < a.s_hi[1]) {
                     const double wy = a.sw[1][c.jw - a.s_lo[1]], wz = a.sw[2][kgB - a.s_lo[2]];
 #pragma unroll
                     for (int q = 0; q < V; ++q) {

@@ -93,6 +93,16 @@ struct Solver {
     std::vector<double> src_amp;
     int src_t = 0;
 
+    // Pending J writes: host writes of J (fdtd_scatter) that arrive while one update_fields() call is recorded but not yet
+    // issued belong to the step AFTER the recorded one.  They are kept as a small dense box per component so that the
+    // next update_fields() can still issue both steps as one two-step pass (stage A reads the J arrays, stage B the box);
+    // the box is written into the arrays right after.  Reference-style loops (`J[idx] = v; update_fields();`,
+    // perf-tests/sample/sample.cpp:66-87) therefore run at the speed of fdtd_step(n).
+    bool jpend = false;
+    int jp_lo[3] = {}, jp_hi[3] = {};
+    void* d_jpend = nullptr;       // 3 components x JPEND_MAX_CELLS elements
+    static constexpr int JPEND_MAX_CELLS = 4096;
+
     // staging for scatter / gather
     void* h_stage = nullptr;       // pinned
     void* d_stage = nullptr;

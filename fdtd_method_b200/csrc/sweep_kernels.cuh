@@ -449,6 +449,34 @@ __global__ void slice_kernel(const T* __restrict__ f, Geom g, int axis, int inde
     }
 }
 
+// Pending J writes (csrc/fdtd_capi.cu): a dense box [lo, hi) of one J component, [k][j][i].
+//   mode 0: box <- array (planes this rank does not own: +0.0)      mode 1: array <- box (owned planes only)
+//   mode 2: box[idx[t]] <- vals[t] for the global flat indices that fall inside the box
+struct JBoxArgs { int lo[3], hi[3]; };
+template <typename T>
+__global__ void jbox_kernel(T* __restrict__ f, Geom g, JBoxArgs b, T* __restrict__ box, int mode,
+                            const long long* __restrict__ idx, const T* __restrict__ vals, int n) {
+    const int ni = b.hi[0] - b.lo[0], nj = b.hi[1] - b.lo[1], nk = b.hi[2] - b.lo[2];
+    if (mode == 2) {
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= n) return;
+        const long long ij = (long long)g.Ni * g.Nj, id = idx[t], r = id % ij;
+        const int k = (int)(id / ij), j = (int)(r / g.Ni), i = (int)(r % g.Ni);
+        if (i < b.lo[0] || i >= b.hi[0] || j < b.lo[1] || j >= b.hi[1] || k < b.lo[2] || k >= b.hi[2]) return;
+        box[((long long)(k - b.lo[2]) * nj + (j - b.lo[1])) * ni + (i - b.lo[0])] = vals[t];
+        return;
+    }
+    const long long total = (long long)ni * nj * nk;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int di = (int)(t % ni), dj = (int)((t / ni) % nj), dk = (int)(t / ((long long)ni * nj));
+        const int k = b.lo[2] + dk - g.k0;
+        const bool owned = k >= 0 && k < g.nk;
+        const long long o = (long long)k * g.plane + (long long)(b.lo[1] + dj) * g.pitch + (b.lo[0] + di);
+        if (mode == 0) box[t] = owned ? f[o] : (T)0;
+        else if (owned) f[o] = box[t];
+    }
+}
+
 // Device-resident current source (fdtd_set_source): J = ((amp*wx)*wy)*wz on a box, the product order of
 // perf-tests/sample/sample.cpp:26-31; `zero` writes +0.0 instead (source expired / zeroed_currents on a box).
 struct SourceArgs {

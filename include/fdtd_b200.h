@@ -147,8 +147,9 @@ fdtd_status_t fdtd_destroy(fdtd_solver_t* s);
  * Asynchronous on the solver's stream; field reads below synchronise as needed.
  * Caller loops that step one call at a time still reach the two-step pass: an odd call is recorded and returns at
  * once, the next call issues both steps together; every other call of this API that reads or changes solver state
- * runs the recorded step first, so the observable sequence is exactly one step per call.  A CUDA error of a recorded
- * step is reported by the call that runs it.  (FDTD_B200_NO_LAZY=1 in the environment issues every call at once.) */
+ * runs the recorded step first, so the observable sequence is exactly one step per call (exception, invisible to the caller:
+ * fdtd_scatter of Jx / Jy / Jz on a small box keeps the writes pending for the second step of the pair).  A CUDA error of a
+ * recorded step is reported by the call that runs it.  (FDTD_B200_NO_LAZY=1 in the environment issues every call at once.) */
 fdtd_status_t fdtd_update_fields(fdtd_solver_t* s);
 
 /* nsteps x update_fields().  Bit-identical to nsteps separate calls. */

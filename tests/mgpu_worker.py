@@ -86,6 +86,20 @@ def main():
                     if not np.array_equal(g.download(c), o.field(c)[kb:ke]):
                         failures += 1
                         print(f"[rank {rank}] MISMATCH mid-run {shape} pml={pml} fusion={fusion} comp {c}", flush=True)
+        # reference-style loop with a J write before every call and no read in between (sample.cpp:66-87): the writes that
+        # arrive while a call is recorded ride into the second stage of the pair as a pending box -- every rank gets the
+        # same global index list; the box straddles the boundary between rank 0 and rank 1
+        if pml is None or fusion:
+            kq = ke0 = (Nk // world) if world > 1 else Nk // 2
+            jidx = np.array([i + j * Ni + k * Ni * Nj for k in (kq - 1, kq) for j in (2, 3) for i in (4, 5, 6)])
+            jidx = jidx[(jidx >= 0) & (jidx < Ni * Nj * Nk)]
+            for t in range(4):
+                for c in (6, 7, 8):
+                    v = (np.arange(jidx.size) * 0.01 + 0.1 * (t + 1) * (c - 5)).astype(dtype)
+                    g.scatter(c, jidx, v)
+                    o.field(c).reshape(-1)[jidx] = v
+                o.update_fields()
+                g.update_fields()
         # batched steps: fdtd_step(n) pairs steps into the temporally blocked T2 pass (two ghost planes per side,
         # J ghost planes included) wherever the slab has >= 4 planes
         o.step(steps + 1)

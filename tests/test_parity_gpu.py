@@ -627,3 +627,48 @@ def test_f32_arith_mode_within_north_star_tolerance(steps):
 def test_f32_arith_needs_float_storage():
     with pytest.raises(TypeError):
         fb.FDTD(params(8, 8, 8), 0.2, dtype=np.float64, f32_arith=True)
+
+
+# ---- pending J writes: reference-style loops with a J write before every update_fields() still pair -----------------------
+@pytest.mark.parametrize("shape,pml,dtype,f32_arith", [((32, 16, 12), None, np.float64, False), ((128, 48, 8), None, np.float64, False),
+                                                        ((64, 24, 16), None, np.float32, False), ((64, 24, 16), None, np.float32, True),
+                                                        ((64, 48, 48), 0.1, np.float64, False)])
+def test_loop_with_J_writes_between_calls_pairs(shape, pml, dtype, f32_arith):
+    """`J[idx] = v; update_fields();` repeated (perf-tests/sample/sample.cpp:66-87): a J write that arrives while one call is
+    recorded becomes a pending box, the next call issues both steps as ONE two-step pass (stage A on the old J, stage B on the
+    box), and every observable state equals the oracle's -- distinct Jx / Jy / Jz on top of a non-zero J background, writes
+    that change every step, a read in the middle, a write outside the box (falls back), zeroed_currents at the end."""
+    Ni, Nj, Nk = shape
+    o, g = make_pair(Ni, Nj, Nk, d=(C, 1.25 * C, 0.8 * C), dtype=dtype, pml=pml, f32_arith=f32_arith)
+    f = seeded_fields(13, (Nk, Nj, Ni), dtype=dtype, same_j=False)
+    load_both(o, g, f)
+    ci, cj, ck = Ni // 2, Nj // 2, Nk // 2
+    idx = np.array([i + j * Ni + k * Ni * Nj for k in (ck - 1, ck) for j in (cj - 1, cj) for i in (ci - 1, ci)])
+    rng = np.random.default_rng(5)
+    p0 = g.info().passes_t2
+    steps = 10
+    for t in range(steps):
+        for c in (6, 7, 8):
+            v = rng.uniform(-1, 1, size=idx.size).astype(dtype)
+            g.get_field(c)[idx] = v
+            o.field(c).reshape(-1)[idx] = v
+        g.update_fields(); o.update_fields()
+    assert g.info().passes_t2 - p0 == steps // 2, "J writes between calls broke the pairing"
+    assert_bit_equal(o, g, comps=range(9), what=f"J-write loop {shape}")
+    # odd call + read in the middle: the recorded step runs alone on the old J, then the arrays take the pending writes
+    for c in (6, 7, 8):
+        g.get_field(c)[idx] = np.full(idx.size, 0.5, dtype=dtype); o.field(c).reshape(-1)[idx] = 0.5
+    g.update_fields(); o.update_fields()
+    for c in (6, 7, 8):
+        g.get_field(c)[idx] = np.full(idx.size, -0.25, dtype=dtype); o.field(c).reshape(-1)[idx] = -0.25
+    assert_bit_equal(o, g, comps=range(9), what="read with a recorded step and pending writes")
+    # a write outside the box while writes are pending -> falls back, same results
+    g.update_fields(); o.update_fields()
+    far = np.array([1 + 2 * Ni + 1 * Ni * Nj])
+    g.get_field(6)[idx] = np.full(idx.size, 0.125, dtype=dtype); o.field(6).reshape(-1)[idx] = 0.125
+    g.get_field(7)[far] = np.array([2.0], dtype=dtype); o.field(7).reshape(-1)[far] = 2.0
+    g.update_fields(); o.update_fields()
+    g.update_fields(); o.update_fields()
+    g.zeroed_currents(); o.zeroed_currents()
+    g.step(3); o.step(3)
+    assert_bit_equal(o, g, comps=range(9), what="after fallback, zeroed_currents and a batch")
