@@ -14,6 +14,8 @@
 #include <new>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost a function-pointer test unless a profiler is attached
+
 #include "fused_kernel.cuh"
 #include "fused_kernel_v2.cuh"
 #include "fused_kernel_t2.cuh"
@@ -603,6 +605,8 @@ static void invalidate_ghosts(Solver* s) {
 // Apply the deferred trailing B half step (main cells only; the PML shell advances once per step).
 static fdtd_status_t flush_pending(Solver* s) {
     if (!s->b_pending) return FDTD_OK;
+    nvtxRangePushA("UpdateBField (deferred trailing half step)");
+    struct Pop { ~Pop() { nvtxRangePop(); } } pop;
     fdtd_status_t st = exchange_E_top(s);
     if (st != FDTD_OK) return st;
     st = DISPATCH_A(s, launch_sweep, s, true, 1, 0);
@@ -823,8 +827,27 @@ static fdtd_status_t advance_pml_pair(Solver* s, int n_half, int src2, double am
     return FDTD_OK;
 }
 
+// NVTX ranges around every launch group, named after the reference's Kokkos kernel labels (kokkos_functors.h:62,126,265,362:
+// "UpdateEField", "UpdateBField", "UpdateEPMLField", "UpdateBPMLField") so that a timeline of this library reads like
+// a Kokkos-tools timeline of the reference.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+static fdtd_status_t advance_impl(Solver* s, int remaining, int* done);
+
 // Advance by one step, or by two when the temporally blocked pass applies; *done = steps advanced.
 static fdtd_status_t advance(Solver* s, int remaining, int* done) {
+    const bool pair = remaining >= 2 && !s->tun.no_t2 && (s->t2 || s->pml_t2);
+    NvtxRange r(s->has_pml ? (pair ? "update_fields x2: UpdateBField+UpdateBPMLField+UpdateEField+UpdateEPMLField (two-step pass + rim sweeps)"
+                                   : "update_fields: UpdateBField+UpdateBPMLField, UpdateEField+UpdateEPMLField (sweeps)")
+                           : (pair ? "update_fields x2: UpdateBField+UpdateEField (fused two-step pass)"
+                                   : "update_fields: UpdateBField+UpdateEField"));
+    return advance_impl(s, remaining, done);
+}
+
+static fdtd_status_t advance_impl(Solver* s, int remaining, int* done) {
     fdtd_status_t st;
     *done = 1;
     // device-resident source: write J for this step (kokkos_sample.cpp:91-108), or retire it (sample.cpp:84)
