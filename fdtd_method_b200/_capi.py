@@ -82,6 +82,7 @@ SIGNATURES = {
     "fdtd_slab_range_cfg": (None, [ctypes.POINTER(Config), _i, _pi, _pi]),
     "fdtd_pml_profile": (_i, [_i, _i, _d, _d, _pd, _pd, _pd]),
     "fdtd_pml_thickness": (_i, [_i, _d]),
+    "fdtd_debug_t2_chunk_plan": (_i, [_i] * 9 + [_pi, _pi, _i]),
     "fdtd_last_error": (ctypes.c_char_p, []),
     "fdtd_version": (_i, []),
 }

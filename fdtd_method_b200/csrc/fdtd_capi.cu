@@ -287,6 +287,62 @@ static fdtd_status_t launch_fused(Solver* s, int n_half, int k_lo, int k_hi) {
 // Variant table <BY rows per CTA, min CTAs/SM>; FDTD_B200_T2_VARIANT picks one.
 struct T2Ranges { int lo, hi, lo2, hi2; };   // local plane ranges a T2 launch produces (second range empty when lo2 == hi2)
 
+// Plane chunks of one T2 launch (host-only, pure: also exported as fdtd_debug_t2_chunk_plan for the CPU test suite).
+//   nk            planes of the rank's slab            rg        the plane range(s) to produce
+//   wait_in_kernel  the kernel waits for the halo itself (slab rank, peer transport): the planes whose dependency cone
+//                 reaches a ghost plane become thin chunks at the END of the list
+//   tiles, gx     working tiles per chunk / tile columns (L2 chunk-length bound)      slots = CTAs resident on the GPU
+// Chunk length.  Every chunk costs 3 redundant plane iterations plus ~2 of start-up, and the CTAs run in waves of one per
+// SM, so the host minimises  waves(m) x (planes per chunk + 5)  over the chunk count m -- long chunks, but a CTA count that
+// fills its last wave (profiles/kc_sweep_r01.jsonl: 3 chunks of 171 beat 4 of 128 at 512^3).  Second constraint: CTAs are
+// dispatched in id order as SMs free up, so the start-time skew between a tile and its y-neighbour (gx ids away) is about
+// (chunk duration) x gx / (CTAs in flight); once it exceeds the time a line survives in L2, the 4 halo rows of every 16-row
+// tile are read from DRAM twice.  Measured (profiles/kc_traffic_r01.jsonl): fine up to len * gx ~ 1540 (512^3, 171 planes:
+// 1.09x compulsory traffic), 1.23x at 2300, 1.37x at 9200 (1024^3 with 512-plane chunks: 87 instead of 110 Gcell/s).
+// Thin boundary chunks (H = the pass's reach, 2 output planes each) are issued LAST, after all interior chunks: by then the
+// neighbours' pushes have long landed, and their short CTAs fill the interior's tail wave.  (A first version kept
+// full-length boundary chunks and lost 11 % in the strong-scaling regime -- 1024^2 planes, two chunks of 64: the top
+// chunk's first wave reached the ghost planes 0.13 ms into the pass, the halo took 0.41 ms, profiles/strong_probe_r02.md.)
+// Each extra chunk costs ~5 plane iterations per tile: 2 % at 512 planes.
+static int t2_chunk_plan(int nk, const T2Ranges& rg, bool wait_in_kernel, long long tiles, int gx, long long slots, int kc_override,
+                         int* chunk_lo, int* chunk_hi) {
+    const int H = 2;
+    int lo = rg.lo, hi = rg.hi;
+    bool thin_top = false, thin_bot = false;
+    if (wait_in_kernel && rg.hi2 <= rg.lo2 && hi - lo >= 4 * H + 8) {
+        thin_bot = lo - 2 < 0;
+        thin_top = hi + 1 >= nk;
+        if (thin_bot) lo += H;
+        if (thin_top) hi -= H;
+    }
+    const int np = hi - lo, np2 = rg.hi2 > rg.lo2 ? rg.hi2 - rg.lo2 : 0;
+    int kc = kc_override;
+    if (kc <= 0) {
+        long long best_cost = -1;
+        int best_m = 1;
+        const int len_cap = std::max(32, 1600 / std::max(gx, 1));
+        for (int m = 1; m <= np; ++m) {
+            const int len = (np + m - 1) / m;
+            if (len > len_cap && len > 32) continue;
+            if (len < 16 && m > 1) break;
+            const int m_eff = (np + len - 1) / len + (np2 > 0 ? (np2 + len - 1) / len : 0);
+            const long long waves = (tiles * m_eff + slots - 1) / slots;
+            const long long cost = waves * (len + 5);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_m = m; }
+        }
+        kc = (np + best_m - 1) / best_m;
+    }
+    if (kc > np) kc = np;
+    if (kc < 1) kc = 1;
+    while ((np + kc - 1) / kc + (np2 + kc - 1) / kc + 2 > T2_MAXCH) ++kc;
+    int gz = 0;
+    for (int k = lo; k < hi; k += kc) { chunk_lo[gz] = k; chunk_hi[gz] = std::min(k + kc, hi); ++gz; }
+    for (int k = rg.lo2; k < rg.hi2; k += kc) { chunk_lo[gz] = k; chunk_hi[gz] = std::min(k + kc, rg.hi2); ++gz; }
+    if (thin_top) { chunk_lo[gz] = hi; chunk_hi[gz] = rg.hi; ++gz; }
+    if (thin_bot) { chunk_lo[gz] = rg.lo; chunk_hi[gz] = lo; ++gz; }
+    return gz;
+}
+
 template <typename T, typename A, int BY, int MINB, int ABL = 0>
 static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, const T2Ranges& rg, int cfg_bit) {
     constexpr int V = t2_v<A>();   // cells per lane: 2 with double arithmetic (both storage types), 4 with float arithmetic
@@ -301,56 +357,10 @@ static cudaError_t launch_t2_variant(Solver* s, FusedT2Args<T>& a, const T2Range
     }
     const int gx = (s->g.Ni + TIU - 1) / TIU;
     const int gy = (s->g.Nj + TJU - 1) / TJU;
-    // Halo wait inside the kernel (one range = the rank's whole slab, possibly clipped by a PML store box): the planes that
-    // read ghost planes are split off as thin chunks (H output planes each, the pass's reach) and issued LAST, after all
-    // interior chunks -- by then the neighbours' pushes have long landed, and their short CTAs fill the interior's tail wave.
-    // (A first version kept full-length boundary chunks and lost 11 % in the strong-scaling regime -- 1024^2 planes, two
-    // chunks of 64: the top chunk's first wave reached the ghost planes 0.13 ms into the pass, the halo took 0.41 ms,
-    // profiles/strong_probe_r02.md.)  Each extra chunk costs ~5 plane iterations per tile: 2 % at 512 planes.
-    const int H = 2;
-    int lo = rg.lo, hi = rg.hi;
-    bool thin_top = false, thin_bot = false;
-    if (a.halo_flags != nullptr && rg.hi2 <= rg.lo2 && hi - lo >= 4 * H + 8) {
-        thin_bot = lo - 2 < 0;
-        thin_top = hi + 1 >= s->g.nk;
-        if (thin_bot) lo += H;
-        if (thin_top) hi -= H;
-    }
-    const int np = hi - lo, np2 = rg.hi2 - rg.lo2;
-    int kc = s->tun.fused_kc;
-    if (kc <= 0) {
-        // Chunk count m of the (first) plane range: every chunk costs 3 redundant plane iterations plus ~2 of start-up,
-        // and the CTAs run in waves of one per SM, so minimise  waves(m) * (planes per chunk + 5)  -- long chunks, but
-        // a CTA count that fills its last wave (profiles/kc_sweep_r01.jsonl: 3 chunks of 171 beat 4 of 128 at 512^3).
-        // (CTAs whose output tile misses the store box exit at once: count the ones that work)
-        const long long tiles = (long long)std::min(gx, (a.sb_hi[0] - a.sb_lo[0] + TIU - 1) / TIU + 1) *
-                                std::min(gy, (a.sb_hi[1] - a.sb_lo[1] + TJU - 1) / TJU + 1), slots = 148LL * MINB;
-        long long best_cost = -1;
-        int best_m = 1;
-        // Second constraint: CTAs are dispatched in id order as SMs free up, so the start-time skew between a tile and
-        // its y-neighbour (gx ids away) is about (chunk duration) x gx / (CTAs in flight); once it exceeds the time a
-        // line survives in L2, the 4 halo rows of every 16-row tile are read from DRAM twice.  Measured
-        // (profiles/kc_traffic_r01.jsonl): fine up to len * gx ~ 1540 (512^3, 171 planes: 1.09x compulsory traffic),
-        // 1.23x at 2300, 1.37x at 9200 (1024^3 with 512-plane chunks: 87 instead of 110 Gcell/s).
-        const int len_cap = std::max(32, 1600 / std::max(gx, 1));
-        for (int m = 1; m <= np; ++m) {
-            const int len = (np + m - 1) / m;
-            if (len > len_cap && len > 32) continue;
-            if (len < 16 && m > 1) break;
-            const int m_eff = (np + len - 1) / len + (np2 > 0 ? (np2 + len - 1) / len : 0);
-            const long long waves = (tiles * m_eff + slots - 1) / slots;
-            const long long cost = waves * (len + 5);
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_m = m; }
-        }
-        kc = (np + best_m - 1) / best_m;
-    }
-    if (kc > np) kc = np;
-    while ((np + kc - 1) / kc + (np2 + kc - 1) / kc + 2 > T2_MAXCH) ++kc;
-    int gz = 0;
-    for (int k = lo; k < hi; k += kc) { a.chunk_lo[gz] = k; a.chunk_hi[gz] = std::min(k + kc, hi); ++gz; }
-    for (int k = rg.lo2; k < rg.hi2; k += kc) { a.chunk_lo[gz] = k; a.chunk_hi[gz] = std::min(k + kc, rg.hi2); ++gz; }
-    if (thin_top) { a.chunk_lo[gz] = hi; a.chunk_hi[gz] = rg.hi; ++gz; }
-    if (thin_bot) { a.chunk_lo[gz] = rg.lo; a.chunk_hi[gz] = lo; ++gz; }
+    // (CTAs whose output tile misses the store box exit at once: count the ones that work)
+    const long long tiles = (long long)std::min(gx, (a.sb_hi[0] - a.sb_lo[0] + TIU - 1) / TIU + 1) *
+                            std::min(gy, (a.sb_hi[1] - a.sb_lo[1] + TJU - 1) / TJU + 1);
+    const int gz = t2_chunk_plan(s->g.nk, rg, a.halo_flags != nullptr, tiles, gx, 148LL * MINB, s->tun.fused_kc, a.chunk_lo, a.chunk_hi);
     a.nchunks = gz;
     a.gx = gx; a.gy = gy;
     {
@@ -1650,6 +1660,13 @@ fdtd_status_t fdtd_comm_init(fdtd_solver_t* h, const void* id, size_t id_bytes) 
     fdtd_status_t st = check_handle(h, &s);
     if (st != FDTD_OK) return st;
     return nccl_init(s, id, id_bytes);
+}
+
+int fdtd_debug_t2_chunk_plan(int nk, int lo, int hi, int lo2, int hi2, int wait_in_kernel, int tiles, int gx, int kc_override,
+                             int* chunk_lo, int* chunk_hi, int capacity) {
+    if (!chunk_lo || !chunk_hi || capacity < T2_MAXCH || hi <= lo) return -1;
+    const T2Ranges rg{lo, hi, lo2, hi2};
+    return t2_chunk_plan(nk, rg, wait_in_kernel != 0, tiles, gx, 148, kc_override, chunk_lo, chunk_hi);
 }
 
 fdtd_status_t fdtd_comm_init_local(fdtd_solver_t** solvers, int n) {

@@ -265,6 +265,11 @@ fdtd_status_t fdtd_pml_profile(int N, int thickness, double d, double dt, double
 /* int(N * pml_percent), FDTD_PML.cpp:254-256 */
 int fdtd_pml_thickness(int N, double pml_percent);
 
+/* Test hook (host-only): the plane-chunk list a two-step-pass launch would use for a slab of nk planes producing [lo, hi)
+ * (and [lo2, hi2)), see csrc/fdtd_capi.cu::t2_chunk_plan.  capacity >= 72.  Returns the number of chunks. */
+int fdtd_debug_t2_chunk_plan(int nk, int lo, int hi, int lo2, int hi2, int wait_in_kernel, int tiles, int gx, int kc_override,
+                             int* chunk_lo, int* chunk_hi, int capacity);
+
 const char* fdtd_last_error(void);
 int fdtd_version(void);
 

@@ -149,3 +149,43 @@ def test_cpp_callers_compile_against_the_headers():
         has_gpu = False
     if not has_gpu:
         assert r.returncode != 0 and "no CUDA device" in r.stdout, r.stdout[-500:]
+
+
+def test_t2_chunk_plan_tiles_every_plane_once():
+    """The plane-chunk list of a two-step-pass launch (csrc/fdtd_capi.cu::t2_chunk_plan, host-only): every plane of the
+    requested range(s) is produced by exactly one chunk, the list fits the kernel's table, and when the kernel waits for the
+    halo itself only the thin chunks at the END of the list reach ghost planes."""
+    import ctypes
+    L = _capi.lib()
+    lo_a, hi_a = (ctypes.c_int * 72)(), (ctypes.c_int * 72)()
+
+    def plan(nk, lo, hi, lo2=0, hi2=0, wait=0, tiles=387, gx=9, kc=0):
+        n = L.fdtd_debug_t2_chunk_plan(nk, lo, hi, lo2, hi2, wait, tiles, gx, kc, lo_a, hi_a, 72)
+        assert 0 < n <= 72, (nk, lo, hi, n)
+        return [(lo_a[i], hi_a[i]) for i in range(n)]
+
+    rng = np.random.default_rng(1)
+    cases = [(512, 0, 512, 0, 0), (1024, 0, 1024, 0, 0), (128, 0, 128, 0, 0), (16, 0, 16, 0, 0), (4, 0, 4, 0, 0), (5, 0, 5, 0, 0),
+             (512, 2, 510, 0, 0), (512, 0, 2, 510, 512), (512, 34, 478, 0, 0), (470, 34, 470, 0, 0), (7, 0, 7, 0, 0)]
+    for _ in range(200):
+        nk = int(rng.integers(4, 1100))
+        lo = int(rng.integers(0, nk - 1)); hi = int(rng.integers(lo + 1, nk + 1))
+        cases.append((nk, lo, hi, 0, 0))
+    for nk, lo, hi, lo2, hi2 in cases:
+        for wait in (0, 1):
+            for tiles, gx in ((387, 9), (1548, 18), (16, 4), (215, 5)):
+                for kc in (0, 7, 64):
+                    ch = plan(nk, lo, hi, lo2, hi2, wait, tiles, gx, kc)
+                    want = sorted(list(range(lo, hi)) + list(range(lo2, hi2)))
+                    got = sorted(k for a, b in ch for k in range(a, b))
+                    assert got == want, (nk, lo, hi, lo2, hi2, wait, ch)
+                    assert all(b > a for a, b in ch)
+                    if wait and hi2 <= lo2 and hi - lo >= 16:
+                        touching = [i for i, (a, b) in enumerate(ch) if a - 2 < 0 or b + 1 >= nk]
+                        n_expected = (1 if lo - 2 < 0 else 0) + (1 if hi + 1 >= nk else 0)
+                        assert touching == list(range(len(ch) - n_expected, len(ch))), (nk, lo, hi, ch)
+                        assert all(ch[i][1] - ch[i][0] == 2 for i in touching)
+    # the benchmarked shapes: 512^3 on one GPU = 3 chunks of 171; a 512-plane slab rank = interior chunks + 2 thin ones
+    assert [b - a for a, b in plan(512, 0, 512)] == [171, 171, 170]
+    p8 = plan(512, 0, 512, wait=1)
+    assert p8[-2:] == [(510, 512), (0, 2)] and p8[0][0] == 2 and p8[-3][1] == 510
