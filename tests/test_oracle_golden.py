@@ -221,3 +221,44 @@ def test_oracle_matches_live_kokkos_reference():
     for c in range(6):
         assert np.array_equal(r.field(c), o.field(c)), NAMES[c]
     r.close()
+
+
+# ---- randomised side-by-side runs against the live reference builds (skipped where oracle/_ref is absent) ----------------
+def test_oracle_matches_live_reference_on_random_small_grids():
+    """Property test: random tiny grids (degenerate extents included), spacings, time steps, step counts and PML
+    percentages -- the restatement equals FDTD_openmp::FDTD / FDTD_PML bit for bit (Jx feeds all three, G1), and its
+    distinct-J mode equals FDTD_kokkos::FDTD on the periodic cases."""
+    from hypothesis import given, settings, strategies as st
+    from oracle.pyoracle import ReferenceKokkos, have_reference_kokkos
+    if not have_reference():
+        pytest.skip("oracle/_ref/libfdtd_ref.so not built here")
+    Reference.set_threads(1)   # G4: the OpenMP PML has a formal data race
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 9), st.integers(1, 9), st.integers(1, 9), st.sampled_from([None, None, 0.1, 0.2, 0.34]),
+           st.integers(1, 5), st.integers(0, 2 ** 31 - 1), st.sampled_from([0.05, 0.2, 0.31]))
+    def run(Ni, Nj, Nk, pml, steps, seed, dt):
+        rng = np.random.default_rng(seed)
+        d = tuple(C * float(v) for v in rng.uniform(0.5, 2.0, size=3))
+        f = [rng.uniform(-1, 1, size=(Nk, Nj, Ni)) for _ in range(9)]
+        r = Reference(Ni, Nj, Nk, d[0], d[1], d[2], dt, pml_percent=pml)
+        o = Oracle(Ni, Nj, Nk, d[0], d[1], d[2], dt, j_mode=J_OPENMP, pml_percent=pml)
+        for c in range(9):
+            r.field(c)[...] = f[c]
+            o.field(c)[...] = f[c]
+        r.step(steps); o.step(steps)
+        for c in range(6):
+            assert np.array_equal(r.field(c), o.field(c)), (Ni, Nj, Nk, pml, steps, NAMES[c])
+        r.close()
+        if pml is None and have_reference_kokkos():
+            k = ReferenceKokkos(Ni, Nj, Nk, d[0], d[1], d[2], dt)
+            q = Oracle(Ni, Nj, Nk, d[0], d[1], d[2], dt, j_mode=J_KOKKOS)
+            for c in range(9):
+                k.field(c)[...] = f[c]
+                q.field(c)[...] = f[c]
+            k.step(steps); q.step(steps)
+            for c in range(6):
+                assert np.array_equal(k.field(c), q.field(c)), ("kokkos", Ni, Nj, Nk, steps, NAMES[c])
+            k.close()
+
+    run()
