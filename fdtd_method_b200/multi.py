@@ -39,12 +39,15 @@ class FDTDMulti:
         self.local_shape = (parameters.Nk, parameters.Nj, parameters.Ni)
         self.local_cells = int(np.prod(self.local_shape))
 
-    def _prep(self, comp=None) -> None:
-        """Before any call that waits for a slab: every slab issues its recorded work (B accesses: the deferred half step
-        too, which is collective) -- a pass of one slab only completes once its neighbours have issued theirs."""
-        b = comp is not None and int(comp) in (3, 4, 5)
+    def _prep(self, comp=None, write: bool = False) -> None:
+        """Before any call that waits for a slab: every slab issues its recorded work -- a pass of one slab only completes
+        once its neighbours have issued theirs.  Accesses that make the library apply the deferred B half step (any access
+        to B, and WRITES of E, include/fdtd_b200.h "COLLECTIVE CALLS") get it issued on every slab here, because it needs
+        the Ex, Ey ring exchange: left to the per-slab call it would be issued on one slab and waited for at once."""
+        c = None if comp is None else int(comp)
+        collective = c is not None and (c in (3, 4, 5) or (write and c < 6))
         for s in self.slabs:
-            s.flush() if b else s.issue()
+            s.flush() if collective else s.issue()
 
     # ---- the reference's public interface ----------------------------------------------------------------
     def get_field(self, this_field) -> FieldView:
@@ -79,7 +82,7 @@ class FDTDMulti:
 
     def upload(self, comp, host: np.ndarray) -> None:
         a = np.ascontiguousarray(host, dtype=self.dtype).reshape(self.local_shape)
-        self._prep(comp)
+        self._prep(comp, write=True)
         for s in self.slabs:
             s.upload(comp, a[s.k_begin:s.k_end])
 
@@ -94,7 +97,7 @@ class FDTDMulti:
         return out
 
     def scatter(self, comp, idx, vals) -> None:
-        self._prep(comp)
+        self._prep(comp, write=True)
         for s in self.slabs:       # every slab gets the global list (the J bounding box must agree on all of them)
             s.scatter(comp, idx, vals)
 

@@ -65,10 +65,14 @@ struct Ring {
         for (fdtd_solver_t* s : h) if (s) fdtd_destroy(s);
     }
     bool is_B(int comp) const { return comp >= 3 && comp <= 5; }
-    // before a call that waits for the device: every slab issues its recorded step (B: and the deferred half step)
-    void prep(int comp) {
+    // Before a call that waits for the device: every slab issues its recorded step.  Accesses that make the library apply
+    // the deferred B half step -- any access to B, and WRITES of E -- get it issued on every slab here: it needs the Ex, Ey
+    // ring exchange, and left to the per-slab call it would be issued on one slab and waited for at once (a deadlock the
+    // random call-sequence test found on E writes).
+    void prep(int comp, bool write = false) {
         if (h.size() == 1) return;
-        for (fdtd_solver_t* s : h) check(is_B(comp) ? fdtd_flush(s) : fdtd_issue(s));
+        const bool collective = is_B(comp) || (write && comp < 6);
+        for (fdtd_solver_t* s : h) check(collective ? fdtd_flush(s) : fdtd_issue(s));
     }
     void download(int comp, FP* host) {
         prep(comp);
@@ -76,14 +80,14 @@ struct Ring {
             check(fdtd_download(h[r], comp, host + (std::size_t)kb[r] * plane, (std::size_t)(ke[r] - kb[r]) * plane));
     }
     void upload(int comp, const FP* host) {
-        prep(comp);
+        prep(comp, true);
         for (std::size_t r = 0; r < h.size(); ++r)
             check(fdtd_upload(h[r], comp, host + (std::size_t)kb[r] * plane, (std::size_t)(ke[r] - kb[r]) * plane));
     }
     // global flat indices: every slab gets the whole list (entries of other slabs are skipped on the device; the
     // bounding box of the non-zero currents must agree on all slabs, fdtd_b200.h "COLLECTIVE CALLS")
     void scatter(int comp, const int64_t* idx, const FP* val, std::size_t n) {
-        prep(comp);
+        prep(comp, true);
         for (fdtd_solver_t* s : h) check(fdtd_scatter(s, comp, idx, val, n));
     }
     void gather(int comp, const int64_t* idx, FP* val, std::size_t n) {

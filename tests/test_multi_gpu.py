@@ -69,3 +69,26 @@ def test_single_process_ring(ngpu, gpu_count):
         for c in range(6):
             assert np.array_equal(g.download(c), o.field(c)), f"{shape} pml={pml} comp {c}"
         g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(240, method="thread")   # a host-side deadlock on the ring blocks inside a CUDA call: fail, do not hang
+@pytest.mark.parametrize("ngpu", [2])
+def test_random_call_sequences_on_the_one_process_ring(ngpu, gpu_count):
+    """The API fuzz of tests/test_parity_gpu.py on FDTDMulti / FDTD_PML_Multi: the same random call sequences with the grid
+    spread over several GPUs in one process (every call fans out; J writes, reads and sources take global indices)."""
+    if gpu_count < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs, have {gpu_count}")
+    import fdtd_method_b200 as fb
+    from oracle.pyoracle import J_KOKKOS, Oracle
+    from tests.util import fuzz_call_sequence, params
+
+    def make(Ni, Nj, Nk, d, dtype, pml, f32_arith):
+        o = Oracle(Ni, Nj, Nk, d[0], d[1], d[2], 0.2, dtype=dtype, j_mode=J_KOKKOS, pml_percent=pml, f32_arith=f32_arith)
+        p = params(Ni, Nj, Nk, *d)
+        kw = dict(devices=list(range(ngpu)), dtype=dtype, f32_arith=f32_arith)
+        g = fb.FDTDMulti(p, 0.2, **kw) if pml is None else fb.FDTD_PML_Multi(p, 0.2, pml, **kw)
+        return o, g
+
+    for seed in range(12):
+        fuzz_call_sequence(seed, make=make, min_nk=4 * ngpu)
