@@ -189,3 +189,28 @@ def test_t2_chunk_plan_tiles_every_plane_once():
     assert [b - a for a, b in plan(512, 0, 512)] == [171, 171, 170]
     p8 = plan(512, 0, 512, wait=1)
     assert p8[-2:] == [(510, 512), (0, 2)] and p8[0][0] == 2 and p8[-3][1] == 510
+
+
+def test_one_process_ring_issues_collective_work_on_every_slab_first():
+    """FDTDMulti._prep (no GPU: mock slabs): before a call that may wait for one slab, every slab issues its recorded work;
+    accesses that make the library apply the deferred B half step -- any B access and WRITES of E -- flush on every slab
+    first (the half step needs the ring exchange; issued on one slab and waited for at once it deadlocks)."""
+    from fdtd_method_b200.multi import FDTDMulti
+
+    class Slab:
+        def __init__(self):
+            self.calls = []
+        def issue(self):
+            self.calls.append("issue")
+        def flush(self):
+            self.calls.append("flush")
+
+    m = FDTDMulti.__new__(FDTDMulti)
+    m.slabs = [Slab(), Slab(), Slab()]
+    expect = {(0, False): "issue", (0, True): "flush", (2, True): "flush", (3, False): "flush", (5, True): "flush",
+              (6, True): "issue", (8, False): "issue", (None, False): "issue"}
+    for (comp, write), want in expect.items():
+        for s in m.slabs:
+            s.calls.clear()
+        m._prep(comp, write=write)
+        assert all(s.calls == [want] for s in m.slabs), (comp, write, [s.calls for s in m.slabs])
